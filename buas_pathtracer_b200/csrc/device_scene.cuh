@@ -1,0 +1,120 @@
+// Device-resident scene + wavefront state layouts (HBM), shared by the kernels and the uploader.
+#pragma once
+#include <stdint.h>
+#include <cuda_runtime.h>
+
+#include "../../include/bpt.h"
+
+namespace bpt {
+
+// ---- acceleration structures -------------------------------------------------------------------------------------
+// Node pairs: the reference allocates BVH children pairwise at even indices (bvh.cpp:259-260, :302-303), so
+// nodes[2k], nodes[2k+1] already form one 64-byte sibling record.  On the device the array is 128-byte aligned
+// and a sibling pair is fetched with four 128-bit loads; pair 0 is {root, zero pad}.  Word layout per node:
+//   q0 = {bv_p.x, bv_p.y, bv_p.z, bv_r.x}   q1 = {bv_r.y, bv_r.z, left_first, count | split_axis << 16}
+struct DNodeHalf { float4 q0; float4 q1; };
+
+// Leaf triangles, leaf order, 48 bytes = 3 x 128-bit:  {a.xyz, original index}  {b-a, 0}  {c-a, 0}.
+// b-a / c-a are the first two operations of ray_intersect_triangle (intersection.cpp:145-146); hoisting them to
+// upload time is exact (same IEEE subtraction, once instead of per test).
+struct DTriangle { float4 a_idx; float4 e1; float4 e2; };
+
+struct DMesh {
+    uint32_t node_base;        // index of this BLAS's node 0 in DScene::blas_nodes
+    uint32_t tri_base;         // index of its first DTriangle in DScene::triangles (also indexes normals)
+    uint32_t triangle_count;
+    uint32_t has_normals;
+};
+
+// Primitive (primitives.h:92-106) flattened; rows 0..2 of the inverse / forward matrices (row 3 is never read
+// on the path: transform() my_math.h:947-954, transform_normal :956-963, translation :975-983).
+struct DPrimitive {
+    float4 inv[3];
+    float4 fwd[3];
+    uint32_t type;
+    uint32_t material;
+    uint32_t mesh;             // index into DScene::meshes (Primitive_Mesh)
+    float    sphere_r;
+    float    box_r[3];
+    uint32_t pad;
+};
+
+struct DPlane { float n[3]; float d; uint32_t material; uint32_t pad[3]; };
+
+struct DMaterial {             // Material (scene.h:15-29) + padding to 80 bytes
+    uint32_t flags;
+    float albedo[3];
+    float checker_color[3];
+    float emission_color[3];
+    float ior, metallic, roughness;
+    int32_t is_participating_medium;
+    float absorb[3];
+    uint32_t pad[3];
+};
+
+struct DScene {
+    const DNodeHalf*  tlas_nodes;
+    const uint32_t*   tlas_indices;
+    const DNodeHalf*  blas_nodes;      // all BLASes back to back
+    const DTriangle*  triangles;       // all meshes back to back, leaf order
+    const float4*     normals;         // 3 x float4 per triangle (leaf order), only for has_normals meshes; may be null
+    const DMesh*      meshes;
+    const DPrimitive* primitives;
+    const DPlane*     planes;
+    const DMaterial*  materials;       // [material_count] + one extra "air" entry (integrators.cpp:597-599)
+    const uint32_t*   lights;
+    const float4*     skydome;         // w*h texels {r,g,b,0}; null -> gradient sky
+    const uint8_t*    strata_perm;     // [256][64]
+    const uint8_t*    bn_sobol;        // [256*256]
+    const uint8_t*    bn_scramble;     // [128*128*8]
+    const uint8_t*    bn_rank;         // [128*128*8]
+    const float*      filter_lut;      // [512]
+
+    uint32_t plane_count, primitive_count, material_count, light_count;
+    uint32_t air_material;             // == material_count
+    uint32_t skydome_w, skydome_h;
+    float top_sky[3], bot_sky[3];
+
+    bpt_camera   camera;               // latched Scene::camera
+    bpt_settings settings;             // latched Scene::settings
+    uint32_t filter_radius;            // FilterCache::kernel_size
+    uint32_t filter_lut_size;          // FilterCache::cache_size (0 = Box)
+    uint32_t film_w, film_h;
+};
+
+// ---- wavefront path state (SoA, one entry per path slot of the current batch) ------------------------------------
+#define BPT_MATERIAL_STACK_DEPTH 64    // integrators.cpp:602
+
+struct DPathState {
+    float4*   ray_o;        // {o.xyz, max_t}
+    float4*   ray_d;        // {d.xyz, unused}
+    float4*   hit;          // {t, prim (bits), tri slot (bits), v}
+    float*    hit_w;        // barycentric w
+    float4*   throughput;   // {xyz, vignette}
+    float4*   radiance;     // {total_color.xyz, unused}
+    uint4*    rng;          // RandomSeries (samplers.h:29-34)
+    float4*   prev_n;       // {prev_N.xyz, bits: flags}   flags: bit0 = is_specular_bounce
+    float2*   jitter;       // AA jitter (raytracer.cpp:444-446)
+    uint8_t*  mstack_at;    // material_stack_at
+    uint16_t* mstack;       // [64][slots] level-major material ids
+    float4*   primary_d;    // {primary ray d.xyz, ray count} (records / vignette)
+    float4*   primary_o;    // only written when records are requested
+};
+
+struct DShadowItem {        // one NEE shadow ray awaiting its occlusion test
+    float4 o_maxt;          // {o.xyz, max_t}
+    float4 d_light;         // {d.xyz, bits: ignored light primitive}
+    float4 contrib_slot;    // {contribution.xyz, bits: slot}
+};
+
+struct DQueues {
+    uint32_t* active[2];    // slot ids for the current / next bounce
+    DShadowItem* shadow;
+    uint32_t* counters;     // [0]=active in, [1]=active out, [2]=shadow count, [3]=trace fetch cursor, [4]=shadow fetch cursor
+};
+
+struct DStats {             // device mirror of bpt_stats
+    unsigned long long v[10];
+};
+
+} // namespace bpt

@@ -1,0 +1,81 @@
+// Host-side scene model of the B200 path-tracing core.
+//
+// Mirrors the *interface* of the reference's Scene (Raytracer/scene.h:91-149) -- same builder calls, same
+// index conventions (material 0 / primitive 0 are null entries, planes live in their own array, lights are
+// PrimitiveIDs) -- but is an index-based, pointer-free model that can be flattened to the device in one pass.
+#pragma once
+#include <stdint.h>
+#include <string>
+#include <vector>
+
+#include "../../include/bpt.h"
+
+namespace bpt {
+
+struct HostBVH {
+    std::vector<bpt_bvh_node> nodes;     // bit-identical to BVH::nodes[0..node_count) (bvh.h:39-45)
+    std::vector<uint32_t>     indices;   // BVH::indices
+};
+
+struct HostMesh {
+    uint32_t triangle_count = 0;
+    bool     has_normals = false;
+    std::vector<float> positions;        // 9 floats per triangle, caller order (Mesh::triangles)
+    std::vector<float> normals;          // 9 floats per triangle, caller order (get_normals(mesh))
+    HostBVH  bvh;                        // MeshBVH (bvh.h:52-58), BVHStorage_Scalar
+    std::vector<float> leaf_triangles;   // MeshBVH::triangles: positions re-ordered into leaf order
+};
+
+struct HostPrimitive {                   // Primitive (primitives.h:92-106) without pointers
+    uint32_t type = BPT_PRIM_NONE;
+    uint32_t material = 0;
+    int32_t  transform = -1;             // index into Scene::transforms, -1 = the shared identity (scene.cpp:76)
+    float    plane_n[3] = {0, 0, 0};
+    float    plane_d = 0;
+    float    sphere_r = 0;
+    float    box_r[3] = {0, 0, 0};
+    uint32_t mesh = 0;
+};
+
+} // namespace bpt
+
+struct bpt_scene {
+    std::vector<bpt_material>       materials;
+    std::vector<uint32_t>           lights;
+    std::vector<bpt::HostPrimitive> planes;
+    std::vector<bpt::HostPrimitive> primitives;
+    std::vector<bpt_m4x4inv>        transforms;
+    std::vector<bpt::HostMesh>      meshes;
+    bpt::HostBVH                    tlas;
+    bool                            has_tlas = false;
+
+    float top_sky_color[3] = {0, 0, 0};
+    float bot_sky_color[3] = {0, 0, 0};
+    uint32_t skydome_w = 0, skydome_h = 0;
+    std::vector<float> skydome;          // w*h*3
+
+    bpt_camera   new_camera{};           // Scene::new_camera (what the user edits)
+    bpt_settings new_settings{};         // Scene::new_settings
+    bpt_filter_cache filter{};           // g_filter_cache (Raytracer.h:42), per scene here
+};
+
+namespace bpt {
+
+void set_error(const char* fmt, ...);
+
+struct SortEntry {                       // BVHSortEntry (bvh.h:25-29)
+    uint32_t index;
+    float p[3];
+    float r[3];
+};
+
+// bvh_build.cpp
+void build_bvh_sah_binned(std::vector<SortEntry>& entries, HostBVH* out);
+void build_mesh_bvh(HostMesh* mesh);
+void build_scene_bvh(bpt_scene* scene);
+
+// host_scene.cpp
+void recompute_camera(bpt_camera* camera);
+const bpt_m4x4inv& identity_transform();
+
+} // namespace bpt

@@ -1,0 +1,721 @@
+// Wavefront kernels of the path-tracing core: ray generation, closest-hit / occlusion traversal, shading
+// (the body of advanced_integrator, Raytracer/integrators.cpp:581-821), and film splatting
+// (render_tile's tail + splat_filter, Raytracer/raytracer.cpp:187-259, :469-488).
+#pragma once
+#include "trace.cuh"
+
+namespace bpt {
+
+// One batch = pixel rows [ya, yb) of the pass rect x samples [sa, sb).  slot = (row-major pixel in batch)*S + (s - sa)
+struct BatchDesc {
+    int32_t  x0, ya;          // first pixel column of the rect / first row of this batch
+    uint32_t rect_w, rows;    // rect width, rows in this batch
+    uint32_t sa, S;           // first sample of this batch, samples per pixel in this batch
+    uint32_t frame_count;     // AccumulationBuffer::frame_count of the pass
+    uint32_t salt;
+    uint32_t slots;           // rect_w*rows*S
+    uint32_t want_records;
+};
+
+BPT_D SamplerCtx make_sampler(const DScene& sc, const BatchDesc& b, uint32_t slot) {
+    uint32_t pix = slot / b.S, s = slot - pix*b.S;
+    SamplerCtx c;
+    c.strata_perm = sc.strata_perm; c.bn_sobol = sc.bn_sobol; c.bn_scramble = sc.bn_scramble; c.bn_rank = sc.bn_rank;
+    c.strategy = sc.settings.sampling_strategy;
+    c.index = b.frame_count + b.sa + s;
+    c.x = (uint32_t)(b.x0 + (int32_t)(pix % b.rect_w));
+    c.y = (uint32_t)(b.ya + (int32_t)(pix / b.rect_w));
+    return c;
+}
+
+// ---- camera (raytracer.cpp:86-123, :372-461) -------------------------------------------------------------------------
+
+BPT_D V2 brown_conrady(V2 uv, float amount, float woh) {
+    uv.y = uv.y / woh;
+    float b1 = 0.1f*amount, b2 = -0.025f*amount;
+    float r2 = uv.x*uv.x + uv.y*uv.y;
+    float s = (1.0f + r2*b1) + r2*r2*b2;
+    uv.x = uv.x*s; uv.y = uv.y*s;
+    uv.y = uv.y*woh;
+    return uv;
+}
+
+BPT_D void apply_lens_distortion(float amount, uint32_t w, uint32_t h, float& u, float& v) {
+    float woh = (float)w / (float)h;
+    V2 zero; zero.x = 0.0f; zero.y = 0.0f;
+    V2 one;  one.x = 1.0f;  one.y = 1.0f;
+    V2 mn = brown_conrady(zero, amount, woh);
+    V2 mx = brown_conrady(one, amount, woh);
+    V2 uv; uv.x = u; uv.y = v;
+    uv = brown_conrady(uv, amount, woh);
+    if (amount > 0.0f) {
+        uv.x = (uv.x - mn.x) / (mn.x + mx.x);
+        uv.y = (uv.y - mn.y) / (mn.y + mx.y);
+    }
+    u = uv.x; v = uv.y;
+}
+
+BPT_D V2 transform_bokeh_sample(V2 o, float f, float n, float phi_shutter_max) {
+    float abx = (o.x*2.0f) - 1.0f, aby = (o.y*2.0f) - 1.0f;
+    float px, py;
+    if ((abx*abx) > (aby*aby)) {
+        px = (fabsf(abx) > 1e-8f) ? ((kPi*0.25f)*(aby / abx)) : 0.0f;
+        py = abx;
+    } else {
+        px = (fabsf(aby) > 1e-8f) ? ((kPi*0.5f) - ((kPi*0.25f)*(abx / aby))) : 0.0f;
+        py = aby;
+    }
+    px += f*phi_shutter_max;
+    float scale = 1.0f;
+    if (f > 0.0f) {
+        float seg = (2.0f*(kPi / n))*floorf(((n*px) + kPi) / (2.0f*kPi));
+        scale = pow_f(cos_f(kPi / n) / cos_f(px - seg), f);
+    }
+    py *= scale;
+    V2 r; r.x = cos_f(px)*py; r.y = sin_f(px)*py;
+    return r;
+}
+
+// ---- shading helpers (integrators.cpp:11-19, :58-119, :235-308) ------------------------------------------------------
+
+BPT_D void get_tangents(V3 n, V3& b1, V3& b2) {
+    float sign = copy_sign(1.0f, n.z);
+    float a = -1.0f / (sign + n.z);
+    float b = n.x*n.y*a;
+    b1 = v3(1.0f + sign*n.x*n.x*a, sign*b, -sign*n.x);
+    b2 = v3(b, sign + n.y*n.y*a, -n.y);
+}
+
+BPT_D V3 oriented_around_normal(V3 v, V3 N) {
+    V3 T, B;
+    get_tangents(N, T, B);
+    return (v.x*B + v.y*N + v.z*T);
+}
+
+BPT_D V3 map_to_hemisphere(V3 N, V2 u) {
+    float azimuth = kTau*u.x;
+    float y = u.y;
+    float s = sqrtf(1.0f - y*y);
+    V3 hemi = v3(cos_f(azimuth)*s, y, sin_f(azimuth)*s);
+    return oriented_around_normal(hemi, N);
+}
+
+BPT_D V3 map_to_cosine_weighted_hemisphere(V3 N, V2 u) {
+    float azimuth = kTau*u.x;
+    float y = u.y;
+    float s = sqrtf(1.0f - y);
+    V3 hemi = v3(cos_f(azimuth)*s, sqrtf(y), sin_f(azimuth)*s);
+    return oriented_around_normal(hemi, N);
+}
+
+BPT_D float fresnel_dielectric(float cos_i, float eta_i, float eta_t, float ratio, float& cos_t_out) {
+    float sin_i = sqrtf(max_t(0.0f, 1.0f - cos_i*cos_i));
+    float sin_t = ratio*sin_i;
+    float cos_t = sqrtf(max_t(0.0f, 1.0f - sin_t*sin_t));
+    cos_t_out = cos_t;
+    if (sin_t >= 1.0f) return 1.0f;
+    float r_par  = (((eta_t*cos_i) - (eta_i*cos_t)) / ((eta_t*cos_i) + (eta_i*cos_t)));
+    float r_perp = (((eta_i*cos_i) - (eta_t*cos_t)) / ((eta_i*cos_i) + (eta_t*cos_t)));
+    return 0.5f*(r_par*r_par + r_perp*r_perp);
+}
+
+BPT_D V3 sample_sky(const DScene& sc, V3 d) {
+    if (sc.skydome) {
+        float rcp_pi = 1.0f / kPi, rcp_2pi = 0.5f / kPi;
+        float phi = atan2_f(d.z, d.x);
+        float theta = asin_f(d.y);
+        float u = 0.5f + rcp_2pi*phi;
+        float v = 0.5f + rcp_pi*theta;
+        int w = (int)sc.skydome_w, h = (int)sc.skydome_h;
+        int sx = (int)(u*(float)w) % w;
+        int sy = (int)(v*(float)h) % h;
+        if (sx < 0) sx = 0;          // the reference reads out of bounds here (Appendix A #9); clamp instead
+        if (sy < 0) sy = 0;
+        float4 px = __ldg(&sc.skydome[sy*w + sx]);
+        return v3(px.x, px.y, px.z);
+    }
+    float sky_t = fabsf(d.y);
+    return lerp_v(v3(sc.bot_sky), v3(sc.top_sky), sky_t);
+}
+
+struct MatView {
+    uint32_t flags;
+    V3 albedo, checker, emission, absorb;
+    float ior, metallic, roughness;
+    int medium;
+};
+
+BPT_D MatView load_material(const DScene& sc, uint32_t id) {
+    const DMaterial* m = sc.materials + id;
+    MatView v;
+    v.flags = __ldg(&m->flags);
+    v.albedo = v3(__ldg(&m->albedo[0]), __ldg(&m->albedo[1]), __ldg(&m->albedo[2]));
+    v.checker = v3(__ldg(&m->checker_color[0]), __ldg(&m->checker_color[1]), __ldg(&m->checker_color[2]));
+    v.emission = v3(__ldg(&m->emission_color[0]), __ldg(&m->emission_color[1]), __ldg(&m->emission_color[2]));
+    v.absorb = v3(__ldg(&m->absorb[0]), __ldg(&m->absorb[1]), __ldg(&m->absorb[2]));
+    v.ior = __ldg(&m->ior); v.metallic = __ldg(&m->metallic); v.roughness = __ldg(&m->roughness);
+    v.medium = __ldg(&m->is_participating_medium);
+    return v;
+}
+
+// :NormalCalculation (intersection.cpp:526-591): hit point + world normal from a hit record
+BPT_D void hit_geometry(const DScene& sc, V3 ro, V3 rd, const HitRecord& h, V3& I, V3& N, uint32_t& material) {
+    float t = h.t;
+    I = ro + t*rd;
+    V3 n = v3(0.0f);
+    if (h.prim & BPT_HIT_PLANE) {
+        const DPlane& pl = sc.planes[h.prim & ~BPT_HIT_PLANE];
+        n = v3(__ldg(&pl.n[0]), __ldg(&pl.n[1]), __ldg(&pl.n[2]));
+        material = __ldg(&pl.material);
+        // planes carry the shared identity transform (scene.cpp:76, :86-90)
+        float4 id[3] = {make_float4(1, 0, 0, 0), make_float4(0, 1, 0, 0), make_float4(0, 0, 1, 0)};
+        N = noz(xform_normal(id, n));
+        return;
+    }
+    const DPrimitive* prim = sc.primitives + h.prim;
+    float4 m[3] = {__ldg(&prim->inv[0]), __ldg(&prim->inv[1]), __ldg(&prim->inv[2])};
+    material = __ldg(&prim->material);
+    uint32_t type = __ldg(&prim->type);
+    if (type == BPT_PRIM_MESH) {
+        const DMesh* mesh = sc.meshes + __ldg(&prim->mesh);
+        if (__ldg(&mesh->has_normals)) {
+            const float4* nt = sc.normals + (size_t)h.tri*3;
+            V3 na = v3(__ldg(&nt[0])), nb = v3(__ldg(&nt[1])), nc = v3(__ldg(&nt[2]));
+            float ux = 1.0f - h.v - h.w;
+            n = (ux*na + h.v*nb + h.w*nc);
+        } else {
+            const DTriangle* tri = sc.triangles + h.tri;
+            V3 e1 = normalize(v3(__ldg(&tri->e1)));
+            V3 e2 = normalize(v3(__ldg(&tri->e2)));
+            n = cross(e1, e2);
+        }
+    } else {
+        V3 oo = xform(m, ro, 1.0f), od = xform(m, rd, 0.0f);
+        V3 op = oo + t*od;
+        if (type == BPT_PRIM_SPHERE) {
+            n = op;
+        } else if (type == BPT_PRIM_BOX) {
+            V3 rel = op / v3(__ldg(&prim->box_r[0]), __ldg(&prim->box_r[1]), __ldg(&prim->box_r[2]));
+            int axis = 0;
+            float largest = fabsf(rel.x);
+            if (fabsf(rel.y) > largest) { axis = 1; largest = fabsf(rel.y); }
+            if (fabsf(rel.z) > largest) { axis = 2; largest = fabsf(rel.z); }
+            n = v3(axis == 0 ? sign_of(rel.x) : 0.0f, axis == 1 ? sign_of(rel.y) : 0.0f, axis == 2 ? sign_of(rel.z) : 0.0f);
+        }
+    }
+    N = noz(xform_normal(m, n));
+}
+
+// ---- kernels ---------------------------------------------------------------------------------------------------------------
+
+// render_tile's per-sample ray setup (raytracer.cpp:372-461) with per-pixel counter-based seeding
+__global__ void __launch_bounds__(256)
+k_raygen(DScene sc, DPathState st, BatchDesc b) {
+    for (uint32_t slot = blockIdx.x*blockDim.x + threadIdx.x; slot < b.slots; slot += gridDim.x*blockDim.x) {
+        SamplerCtx sm = make_sampler(sc, b, slot);
+        uint4 rng = random_seed(hash_coordinate3(sm.x, sm.y, sm.index) ^ b.salt);
+
+        const bpt_camera& cam = sc.camera;
+        V3 cam_p = v3(cam.p), cam_x = v3(cam.x), cam_y = v3(cam.y), cam_z = v3(cam.z);
+        float focus = cam.focus_distance, lens_radius = cam.lens_radius;
+        float half_w = cam.half_film_w*focus, half_h = cam.half_film_h*focus;
+        float film_distance = focus*cam.film_distance;
+        V3 film_center = (cam_p - film_distance*cam_z);
+        float pixel_w = 1.0f / (float)sc.film_w, pixel_h = 1.0f / (float)sc.film_h;
+
+        float v = 1.0f - 2.0f*(float)(int32_t)sm.y*pixel_h;
+        float u = 1.0f - 2.0f*(float)(int32_t)sm.x*pixel_w;
+        apply_lens_distortion(sc.settings.lens_distortion, sc.film_w, sc.film_h, u, v);
+
+        V2 aa = sample_2d(sm, rng, Sample_AA, 0);
+        float jx = aa.x - 0.5f, jy = aa.y - 0.5f;
+        V2 dof = sample_2d(sm, rng, Sample_DOF, 0);
+        dof = transform_bokeh_sample(dof, sc.settings.f_factor, sc.settings.diaphragm_edges, kPi*sc.settings.phi_shutter_max);
+        float dof_x = half_w*pixel_w*lens_radius*dof.x;
+        float dof_y = half_h*pixel_h*lens_radius*dof.y;
+
+        V3 film_p = film_center;
+        film_p = film_p + (u + pixel_w*jx)*half_w*cam_x;
+        film_p = film_p + (v + pixel_h*jy)*half_h*cam_y;
+        V3 lens_p = (cam_p + dof_x*cam_x + dof_y*cam_y);
+        V3 ray_o = lens_p;
+        V3 ray_d = normalize(film_p - lens_p);
+
+        float vignette = dot(ray_d, cam_z);
+        vignette = vignette*vignette*vignette*vignette;
+        vignette = lerp_f(1.0f, vignette, sc.settings.vignette_strength);
+
+        st.ray_o[slot] = make_float4(ray_o.x, ray_o.y, ray_o.z, 3.402823466e+38f);    // make_ray's FLT_MAX far clip
+        st.ray_d[slot] = make_float4(ray_d.x, ray_d.y, ray_d.z, 0.0f);
+        st.throughput[slot] = make_float4(1.0f, 1.0f, 1.0f, vignette);
+        st.radiance[slot] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        st.rng[slot] = rng;
+        st.prev_n[slot] = make_float4(0.0f, 0.0f, 0.0f, __uint_as_float(1u));          // is_specular_bounce = true
+        st.jitter[slot] = make_float2(jx, jy);
+        st.mstack_at[slot] = 0;
+        st.mstack[slot] = (uint16_t)sc.air_material;                                    // material_stack[0] = &air
+        st.primary_d[slot] = make_float4(ray_d.x, ray_d.y, ray_d.z, 0.0f);
+        if (b.want_records) st.primary_o[slot] = make_float4(ray_o.x, ray_o.y, ray_o.z, 0.0f);
+    }
+}
+
+BPT_D void flush_counters(DStats* stats, const TraceCounters& c, uint32_t rays, uint32_t shadow) {
+    // warp-aggregate, then one atomic per counter per warp
+    unsigned long long vals[9] = {rays, shadow, c.tlas_pops, c.instances, c.mesh_calls, c.blas_pops, c.blas_inner, c.blas_leaves, c.tris};
+    #pragma unroll
+    for (int k = 0; k < 9; ++k) {
+        unsigned long long v = vals[k];
+        #pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
+        if ((threadIdx.x & 31) == 0 && v) atomicAdd(&stats->v[k], v);
+    }
+}
+
+// intersect_scene for every active path (integrators.cpp:615).  in_queue == nullptr means "slot = i".
+template <bool STATS>
+__global__ void __launch_bounds__(128)
+k_trace_closest(DScene sc, DPathState st, const uint32_t* __restrict__ in_queue, const uint32_t* __restrict__ n_ptr,
+                uint32_t n_fixed, DStats* stats) {
+    uint32_t n = n_ptr ? *n_ptr : n_fixed;
+    TraceCounters ctr = {};
+    uint32_t rays = 0;
+    uint32_t stride = gridDim.x*blockDim.x;
+    uint32_t base = blockIdx.x*blockDim.x + threadIdx.x;
+    // whole warps iterate together so the stats shuffle stays converged
+    for (uint32_t i0 = base - (threadIdx.x & 31); i0 < n; i0 += stride) {
+        uint32_t i = i0 + (threadIdx.x & 31);
+        if (i < n) {
+            uint32_t slot = in_queue ? in_queue[i] : i;
+            float4 o = st.ray_o[slot], d = st.ray_d[slot];
+            HitRecord h;
+            trace_ray<false, STATS>(sc, v3(o), v3(d), o.w, 0u, h, ctr);
+            st.hit[slot] = make_float4(h.t, __uint_as_float(h.prim), __uint_as_float(h.tri), h.v);
+            st.hit_w[slot] = h.w;
+            rays += 1;
+        }
+    }
+    if (STATS) flush_counters(stats, ctr, rays, 0);
+}
+
+// intersect_shadow_ray for every queued NEE sample (integrators.cpp:756); unoccluded -> add the pending contribution
+template <bool STATS>
+__global__ void __launch_bounds__(128)
+k_trace_shadow(DScene sc, DPathState st, const DShadowItem* __restrict__ items, const uint32_t* __restrict__ n_ptr, DStats* stats) {
+    uint32_t n = *n_ptr;
+    TraceCounters ctr = {};
+    uint32_t rays = 0;
+    uint32_t stride = gridDim.x*blockDim.x;
+    uint32_t base = blockIdx.x*blockDim.x + threadIdx.x;
+    for (uint32_t i0 = base - (threadIdx.x & 31); i0 < n; i0 += stride) {
+        uint32_t i = i0 + (threadIdx.x & 31);
+        if (i < n) {
+            float4 o = items[i].o_maxt, d = items[i].d_light, c = items[i].contrib_slot;
+            HitRecord h;
+            trace_ray<true, STATS>(sc, v3(o), v3(d), o.w, __float_as_uint(d.w), h, ctr);
+            rays += 1;
+            if (h.prim == BPT_HIT_MISS) {
+                uint32_t slot = __float_as_uint(c.w);
+                float4 r = st.radiance[slot];
+                r.x = r.x + c.x; r.y = r.y + c.y; r.z = r.z + c.z;
+                st.radiance[slot] = r;
+            }
+        }
+    }
+    if (STATS) flush_counters(stats, ctr, rays, rays);
+}
+
+// warp-aggregated append: returns this lane's index in the destination queue
+BPT_D uint32_t queue_append(uint32_t* counter, bool want) {
+    uint32_t mask = __ballot_sync(__activemask(), want);
+    if (!want) return 0;
+    uint32_t lane = threadIdx.x & 31;
+    uint32_t leader = __ffs(mask) - 1;
+    uint32_t base = 0;
+    if (lane == leader) base = atomicAdd(counter, __popc(mask));
+    base = __shfl_sync(mask, base, leader);
+    return base + __popc(mask & ((1u << lane) - 1u));
+}
+
+// One bounce of advanced_integrator (integrators.cpp:612-818) for every active path.
+__global__ void __launch_bounds__(128)
+k_shade(DScene sc, DPathState st, BatchDesc b, uint32_t bounce,
+        const uint32_t* __restrict__ in_queue, const uint32_t* __restrict__ n_ptr, uint32_t n_fixed,
+        uint32_t* __restrict__ out_queue, uint32_t* out_count,
+        DShadowItem* __restrict__ shadow_items, uint32_t* shadow_count) {
+    uint32_t n = n_ptr ? *n_ptr : n_fixed;
+    uint32_t stride = gridDim.x*blockDim.x;
+    uint32_t base = blockIdx.x*blockDim.x + threadIdx.x;
+    const bpt_settings& set = sc.settings;
+
+    for (uint32_t i0 = base - (threadIdx.x & 31); i0 < n; i0 += stride) {
+        uint32_t i = i0 + (threadIdx.x & 31);
+        bool alive = false;          // path continues to the next bounce
+        bool want_shadow = false;
+        uint32_t slot = 0;
+        DShadowItem sh;
+
+        if (i < n) {
+            slot = in_queue ? in_queue[i] : i;
+            float4 ro4 = st.ray_o[slot], rd4 = st.ray_d[slot], h4 = st.hit[slot];
+            V3 ro = v3(ro4), rd = v3(rd4);
+            HitRecord h;
+            h.t = h4.x; h.prim = __float_as_uint(h4.y); h.tri = __float_as_uint(h4.z); h.v = h4.w; h.w = st.hit_w[slot];
+            float4 tp4 = st.throughput[slot];
+            V3 throughput = v3(tp4);
+            float4 rad4 = st.radiance[slot];
+            V3 total = v3(rad4);
+            float4 pd = st.primary_d[slot];
+            uint32_t ray_count = __float_as_uint(pd.w) + 1u;      // this bounce's intersect_scene call
+
+            if (h.prim == BPT_HIT_MISS) {
+                total = total + throughput*sample_sky(sc, rd);                                     // :813
+            } else {
+                SamplerCtx sm = make_sampler(sc, b, slot);
+                uint4 rng = st.rng[slot];
+                float4 pn4 = st.prev_n[slot];
+                V3 prev_N = v3(pn4);
+                bool is_specular = (__float_as_uint(pn4.w) & 1u) != 0;
+                int stack_at = st.mstack_at[slot];
+
+                V3 I, N;
+                uint32_t surface_id;
+                hit_geometry(sc, ro, rd, h, I, N, surface_id);
+                float t = h.t;
+
+                float cos_i = -dot(rd, N);                                                          // :618
+                bool inside = (cos_i < 0.0f);
+                uint32_t id_i, id_t;
+                if (inside) {
+                    id_i = surface_id;
+                    int below = stack_at - 1; if (below < 0) below = 0;
+                    id_t = st.mstack[(size_t)below*b.slots + slot];
+                    cos_i = -cos_i;
+                    N = -N;
+                } else {
+                    id_i = st.mstack[(size_t)stack_at*b.slots + slot];
+                    id_t = surface_id;
+                }
+                MatView mi = load_material(sc, id_i);
+                MatView mt = load_material(sc, id_t);
+
+                if (mi.medium) {                                                                     // :640-649 Beer
+                    V3 absorption = v3(exp_f(-mi.absorb.x*t), exp_f(-mi.absorb.y*t), exp_f(-mi.absorb.z*t));
+                    throughput = throughput*absorption;
+                }
+
+                if (mt.flags & BPT_MATERIAL_EMISSIVE) {                                              // :651-670
+                    bool allow_direct = (!set.next_event_estimation ||
+                                         ((set.caustics || (bounce < 2)) && is_specular));
+                    if (allow_direct) {
+                        total = total + throughput*mt.emission;
+                    } else if (bounce > 0 && set.use_mis) {
+                        float light_distance_sq = t*t;
+                        float light_pdf = light_distance_sq / cos_i;
+                        float brdf_pdf = (set.importance_sample_diffuse ? dot(prev_N, rd) / kPi : 1.0f / (2.0f*kPi));
+                        float mis_pdf = light_pdf + brdf_pdf;
+                        total = total + (1.0f / mis_pdf)*throughput*mt.emission;
+                    }
+                } else {
+                    alive = true;
+                    float eta_i = mi.ior, eta_t = mt.ior;
+                    float ratio = eta_i / eta_t;
+                    float cos_t;
+                    float reflectance = fresnel_dielectric(cos_i, eta_i, eta_t, ratio, cos_t);
+                    float reflect_test = sample_1d(sm, rng, Sample_Reflectance, bounce);
+                    reflectance = lerp_f(reflectance, 1.0f, mt.metallic);
+                    is_specular = true;
+                    V3 next_o, next_d;
+
+                    if (reflect_test < reflectance) {                                                // :684-696
+                        V3 refl = reflect(rd, N);
+                        if (mt.roughness > 0.0f) {
+                            V3 rs;
+                            do {                                                                     // random_in_unit_sphere :11-19
+                                next_set(rng);
+                                rs = v3(bilateral(rng.x), bilateral(rng.y), bilateral(rng.z));
+                            } while (length_sq(rs) >= 1.0f);
+                            refl = normalize((1.0f + kEps)*refl + mt.roughness*rs);
+                        }
+                        next_o = I + kEps*refl; next_d = refl;
+                        throughput = throughput*lerp_v(v3(1.0f), mt.albedo, mt.metallic);
+                    } else if (mt.medium) {                                                          // :698-717 refract
+                        if (inside) {
+                            if (stack_at > 0) --stack_at;
+                        } else if (stack_at < (BPT_MATERIAL_STACK_DEPTH - 1)) {
+                            ++stack_at;
+                            st.mstack[(size_t)stack_at*b.slots + slot] = (uint16_t)id_t;
+                        }
+                        V3 refr = ratio*rd + N*(ratio*cos_i - cos_t);
+                        next_o = I + refr*kEps; next_d = refr;
+                    } else {                                                                         // :719-790 diffuse
+                        is_specular = false;
+                        V3 albedo = mt.albedo;
+                        if (mt.flags & BPT_MATERIAL_CHECKERS) {
+                            int checker = (((int)floorf(0.25f*I.x)) ^ ((int)floorf(0.25f*I.z))) & 1;
+                            if (checker) albedo = mt.checker;
+                        }
+                        V3 brdf = (1.0f / kPi)*albedo;
+
+                        if (set.next_event_estimation && (sc.light_count > 0)) {
+                            float pick = sample_1d(sm, rng, Sample_LightSelection, bounce);
+                            // pick_random_light (:135-192)
+                            uint32_t light_id = 0;
+                            float pick_pdf = 0.0f;
+                            if (set.importance_sample_lights) {
+                                float sum = 0.0f;
+                                for (uint32_t li = 0; li < sc.light_count; ++li) {
+                                    const DPrimitive* lp = sc.primitives + __ldg(&sc.lights[li]);
+                                    V3 lv = v3(__ldg(&lp->fwd[0].w), __ldg(&lp->fwd[1].w), __ldg(&lp->fwd[2].w)) - I;
+                                    float dsq = length_sq(lv);
+                                    const DMaterial* lm = sc.materials + __ldg(&lp->material);
+                                    float l = max3(v3(__ldg(&lm->emission_color[0]), __ldg(&lm->emission_color[1]), __ldg(&lm->emission_color[2])));
+                                    float r = __ldg(&lp->sphere_r);
+                                    float psa = (__ldg(&lp->type) == BPT_PRIM_SPHERE) ? (kPi*r*r / dsq) : 0.0f;
+                                    sum += l*psa;
+                                }
+                                float e = sum*pick;
+                                float cdf = 0.0f, pdf = 0.0f;
+                                uint32_t li = 0;
+                                for (;; ++li) {
+                                    const DPrimitive* lp = sc.primitives + __ldg(&sc.lights[li]);
+                                    V3 lv = v3(__ldg(&lp->fwd[0].w), __ldg(&lp->fwd[1].w), __ldg(&lp->fwd[2].w)) - I;
+                                    float dsq = length_sq(lv);
+                                    const DMaterial* lm = sc.materials + __ldg(&lp->material);
+                                    float l = max3(v3(__ldg(&lm->emission_color[0]), __ldg(&lm->emission_color[1]), __ldg(&lm->emission_color[2])));
+                                    float r = __ldg(&lp->sphere_r);
+                                    float psa = (__ldg(&lp->type) == BPT_PRIM_SPHERE) ? (kPi*r*r / dsq) : 0.0f;
+                                    pdf = l*psa;
+                                    cdf = cdf + pdf;
+                                    if (!(cdf < e) || li + 1 >= sc.light_count) break;
+                                }
+                                pick_pdf = pdf / sum;
+                                light_id = __ldg(&sc.lights[li]);
+                            } else {
+                                pick_pdf = 1.0f / (float)sc.light_count;
+                                uint32_t li = (uint32_t)(pick*(float)sc.light_count - kEps);
+                                light_id = __ldg(&sc.lights[li]);
+                            }
+
+                            V2 ds = sample_2d(sm, rng, Sample_DirectLighting, bounce);
+                            const DPrimitive* lp = sc.primitives + light_id;
+                            if (__ldg(&lp->type) == BPT_PRIM_SPHERE) {
+                                // random_point_on_light (:199-228)
+                                float4 f[3] = {__ldg(&lp->fwd[0]), __ldg(&lp->fwd[1]), __ldg(&lp->fwd[2])};
+                                float lr = __ldg(&lp->sphere_r);
+                                V3 light_p = v3(f[0].w, f[1].w, f[2].w);
+                                V3 towards = normalize(light_p - I);
+                                V3 Nl = map_to_hemisphere(-towards, ds);
+                                V3 p = Nl*lr;
+                                V3 p_world = xform(f, p, 1.0f);
+                                V3 L = p_world - I;
+                                float dist_sq = length_sq(L);
+                                float dist = sqrtf(dist_sq);
+                                L = L / dist;
+                                float A = 2.0f*kPi*lr*lr;
+
+                                float N_dot_L = dot(N, L);
+                                float neg_Nl_dot_L = -dot(Nl, L);
+                                if (N_dot_L > 0.0f && neg_Nl_dot_L > 0.0f) {
+                                    float solid_angle = (neg_Nl_dot_L*A) / dist_sq;
+                                    float pdf;
+                                    if (set.use_mis) {
+                                        float light_pdf = 1.0f / solid_angle;
+                                        float brdf_pdf = (set.importance_sample_diffuse ? N_dot_L / kPi : 1.0f / (2.0f*kPi));
+                                        pdf = light_pdf + brdf_pdf;
+                                    } else {
+                                        pdf = 1.0f / solid_angle;
+                                    }
+                                    pdf *= pick_pdf;
+                                    const DMaterial* lm = sc.materials + __ldg(&lp->material);
+                                    V3 emission = v3(__ldg(&lm->emission_color[0]), __ldg(&lm->emission_color[1]), __ldg(&lm->emission_color[2]));
+                                    V3 contrib = throughput*(dot(N, L) / pdf)*brdf*emission;
+                                    V3 so = I + L*kEps;
+                                    sh.o_maxt = make_float4(so.x, so.y, so.z, dist - 2*kEps);
+                                    sh.d_light = make_float4(L.x, L.y, L.z, __uint_as_float(light_id));
+                                    sh.contrib_slot = make_float4(contrib.x, contrib.y, contrib.z, __uint_as_float(slot));
+                                    want_shadow = true;
+                                    ray_count += 1u;
+                                }
+                            }
+                        }
+
+                        V2 is = sample_2d(sm, rng, Sample_IndirectLighting, bounce);
+                        V3 R;
+                        if (set.importance_sample_diffuse) {
+                            R = map_to_cosine_weighted_hemisphere(N, is);
+                            throughput = throughput*kPi;
+                        } else {
+                            R = map_to_hemisphere(N, is);
+                            throughput = throughput*(2.0f*kPi*dot(N, R));
+                        }
+                        throughput = throughput*brdf;
+                        next_o = I + N*kEps; next_d = R;
+                    }
+
+                    if (set.russian_roulette && !is_specular) {                                      // :801-811
+                        float p = clamp_t(max3(throughput), 0.1f, 0.9f);
+                        float e = sample_1d(sm, rng, Sample_Roulette, bounce);
+                        if (e > p) alive = false;
+                        else throughput = throughput*(1.0f / p);
+                    }
+
+                    if (bounce + 1 >= set.max_bounce_count) alive = false;
+                    if (alive) {
+                        st.ray_o[slot] = make_float4(next_o.x, next_o.y, next_o.z, 3.402823466e+38f);
+                        st.ray_d[slot] = make_float4(next_d.x, next_d.y, next_d.z, 0.0f);
+                        st.rng[slot] = rng;
+                        st.prev_n[slot] = make_float4(N.x, N.y, N.z, __uint_as_float(is_specular ? 1u : 0u));
+                        st.mstack_at[slot] = (uint8_t)stack_at;
+                        st.throughput[slot] = make_float4(throughput.x, throughput.y, throughput.z, tp4.w);
+                    }
+                }
+            }
+            st.radiance[slot] = make_float4(total.x, total.y, total.z, 0.0f);
+            pd.w = __uint_as_float(ray_count);
+            st.primary_d[slot] = pd;
+        }
+
+        uint32_t qi = queue_append(out_count, alive);
+        if (alive) out_queue[qi] = slot;
+        uint32_t si = queue_append(shadow_count, want_shadow);
+        if (want_shadow) shadow_items[si] = sh;
+    }
+}
+
+// render_tile's tail (raytracer.cpp:469-488) + splat_filter (:187-259): one thread per pixel of the batch walks that
+// pixel's samples, keeps the (2r+1)^2 footprint in registers, and flushes it with vector atomics.
+template <int R>
+__global__ void __launch_bounds__(128)
+k_splat(DScene sc, DPathState st, BatchDesc b, float4* __restrict__ film) {
+    constexpr int SPAN = 2*R + 1;
+    uint32_t pixels = b.rect_w*b.rows;
+    for (uint32_t pix = blockIdx.x*blockDim.x + threadIdx.x; pix < pixels; pix += gridDim.x*blockDim.x) {
+        int x = b.x0 + (int)(pix % b.rect_w), y = b.ya + (int)(pix / b.rect_w);
+        float4 acc[SPAN*SPAN];
+        #pragma unroll
+        for (int k = 0; k < SPAN*SPAN; ++k) acc[k] = make_float4(0, 0, 0, 0);
+        float kernel_scale = (float)(sc.filter_lut_size - 1) / (float)sc.filter_radius;
+        for (uint32_t s = 0; s < b.S; ++s) {
+            uint32_t slot = pix*b.S + s;
+            float4 rad = st.radiance[slot];
+            float vig = st.throughput[slot].w;
+            float2 j = st.jitter[slot];
+            V3 c = v3(rad)*vig;
+            float wx[SPAN], wy[SPAN];
+            #pragma unroll
+            for (int i = 0; i < SPAN; ++i) {
+                int ix = (int)fabsf(0.5f + kernel_scale*((float)(i - R) - j.x));
+                int iy = (int)fabsf(0.5f + kernel_scale*((float)(i - R) - j.y));
+                wx[i] = __ldg(&sc.filter_lut[ix]);
+                wy[i] = __ldg(&sc.filter_lut[iy]);
+            }
+            #pragma unroll
+            for (int yy = 0; yy < SPAN; ++yy) {
+                #pragma unroll
+                for (int xx = 0; xx < SPAN; ++xx) {
+                    float f = wx[xx]*wy[yy];
+                    float4& a = acc[yy*SPAN + xx];
+                    a.x = a.x + f*c.x; a.y = a.y + f*c.y; a.z = a.z + f*c.z; a.w = a.w + f;
+                }
+            }
+        }
+        #pragma unroll
+        for (int yy = 0; yy < SPAN; ++yy) {
+            int py = y + yy - R;
+            if (py < 0 || py >= (int)sc.film_h) continue;
+            #pragma unroll
+            for (int xx = 0; xx < SPAN; ++xx) {
+                int px = x + xx - R;
+                if (px < 0 || px >= (int)sc.film_w) continue;
+                atomicAdd(&film[(size_t)py*sc.film_w + px], acc[yy*SPAN + xx]);
+            }
+        }
+    }
+}
+
+// generic-radius splat (filters up to r = 12) and the Box path (raytracer.cpp:485-488); one thread per sample
+__global__ void __launch_bounds__(128)
+k_splat_generic(DScene sc, DPathState st, BatchDesc b, float4* __restrict__ film) {
+    int R = (int)sc.filter_radius;
+    for (uint32_t slot = blockIdx.x*blockDim.x + threadIdx.x; slot < b.slots; slot += gridDim.x*blockDim.x) {
+        uint32_t pix = slot / b.S;
+        int x = b.x0 + (int)(pix % b.rect_w), y = b.ya + (int)(pix / b.rect_w);
+        float4 rad = st.radiance[slot];
+        float vig = st.throughput[slot].w;
+        V3 c = v3(rad)*vig;
+        if (sc.filter_lut_size == 0) {
+            atomicAdd(&film[(size_t)y*sc.film_w + x], make_float4(c.x, c.y, c.z, 1.0f));
+            continue;
+        }
+        float2 j = st.jitter[slot];
+        float kernel_scale = (float)(sc.filter_lut_size - 1) / (float)sc.filter_radius;
+        for (int yy = 0; yy <= 2*R; ++yy) {
+            int py = y + yy - R;
+            if (py < 0 || py >= (int)sc.film_h) continue;
+            float fy = __ldg(&sc.filter_lut[(int)fabsf(0.5f + kernel_scale*((float)(yy - R) - j.y))]);
+            for (int xx = 0; xx <= 2*R; ++xx) {
+                int px = x + xx - R;
+                if (px < 0 || px >= (int)sc.film_w) continue;
+                float fx = __ldg(&sc.filter_lut[(int)fabsf(0.5f + kernel_scale*((float)(xx - R) - j.x))]);
+                float f = fx*fy;
+                atomicAdd(&film[(size_t)py*sc.film_w + px], make_float4(f*c.x, f*c.y, f*c.z, f));
+            }
+        }
+    }
+}
+
+__global__ void k_write_records(DPathState st, BatchDesc b, bpt_sample_record* __restrict__ out) {
+    for (uint32_t slot = blockIdx.x*blockDim.x + threadIdx.x; slot < b.slots; slot += gridDim.x*blockDim.x) {
+        float4 o = st.primary_o[slot], d = st.primary_d[slot], r = st.radiance[slot];
+        bpt_sample_record rec;
+        rec.ray_o[0] = o.x; rec.ray_o[1] = o.y; rec.ray_o[2] = o.z;
+        rec.ray_d[0] = d.x; rec.ray_d[1] = d.y; rec.ray_d[2] = d.z;
+        rec.radiance[0] = r.x; rec.radiance[1] = r.y; rec.radiance[2] = r.z;
+        rec.rays = __float_as_uint(d.w);
+        out[slot] = rec;
+    }
+}
+
+// bpt_trace: host ray batch -> bpt_hit (diagnostics / parity), closest or occlusion
+template <bool OCC, bool STATS>
+__global__ void __launch_bounds__(128)
+k_trace_api(DScene sc, const bpt_ray* __restrict__ rays, uint32_t n, uint32_t ignored, bpt_hit* __restrict__ out,
+            const uint32_t* __restrict__ tri_original, DStats* stats) {
+    TraceCounters ctr = {};
+    uint32_t cnt = 0;
+    uint32_t stride = gridDim.x*blockDim.x;
+    uint32_t base = blockIdx.x*blockDim.x + threadIdx.x;
+    for (uint32_t i0 = base - (threadIdx.x & 31); i0 < n; i0 += stride) {
+        uint32_t i = i0 + (threadIdx.x & 31);
+        if (i < n) {
+            bpt_ray r = rays[i];
+            V3 o = v3(r.o), d = v3(r.d);
+            HitRecord h;
+            trace_ray<OCC, STATS>(sc, o, d, r.max_t, OCC ? ignored : 0u, h, ctr);
+            cnt += 1;
+            bpt_hit res;
+            res.t = OCC ? r.max_t : h.t;
+            res.primitive = h.prim;
+            res.triangle = 0xFFFFFFFFu;
+            res.n[0] = res.n[1] = res.n[2] = 0.0f;
+            res.p[0] = res.p[1] = res.p[2] = 0.0f;
+            if (!OCC && h.prim != BPT_HIT_MISS) {
+                V3 I, N; uint32_t mat;
+                hit_geometry(sc, o, d, h, I, N, mat);
+                res.n[0] = N.x; res.n[1] = N.y; res.n[2] = N.z;
+                res.p[0] = I.x; res.p[1] = I.y; res.p[2] = I.z;
+                if (h.tri != 0xFFFFFFFFu && !(h.prim & BPT_HIT_PLANE) && sc.primitives[h.prim].type == BPT_PRIM_MESH) {
+                    res.triangle = tri_original[h.tri];
+                }
+            }
+            out[i] = res;
+        }
+    }
+    if (STATS) flush_counters(stats, ctr, cnt, OCC ? cnt : 0);
+}
+
+__global__ void k_reset_counters(uint32_t* counters, int which_mask) {
+    if (threadIdx.x < 8 && (which_mask >> threadIdx.x) & 1) counters[threadIdx.x] = 0;
+}
+
+} // namespace bpt

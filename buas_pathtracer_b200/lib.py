@@ -1,0 +1,214 @@
+"""Loader + object wrappers for libbpt.so (the product library)."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from . import capi
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+# every symbol include/bpt.h declares (checked by tests/test_abi.py against the header itself)
+DEVICE_SYMBOLS = [
+    "create", "destroy", "set_sampler_tables", "upload_scene", "update_settings", "film_resize", "film_clear",
+    "film_use_external", "film_device_ptr", "download_film", "render_pass", "sync", "trace", "set_sample_records",
+    "stats_enable", "get_stats", "get_pass_timing",
+]
+MISC_SYMBOLS = ["last_error", "version", "make_displaced_icosphere", "make_procedural_skydome"]
+
+
+class BptError(RuntimeError):
+    pass
+
+
+def library_path():
+    return os.path.join(HERE, "libbpt.so")
+
+
+def build_library(force=False):
+    """Compile libbpt.so in-tree with nvcc for sm_100a (works without a GPU)."""
+    args = ["make", "-C", os.path.join(HERE, "csrc")] + (["-B"] if force else [])
+    r = subprocess.run(args, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if r.returncode != 0:
+        raise BptError("building libbpt.so failed:\n" + r.stdout)
+    return library_path()
+
+
+def load_library():
+    """dlopen libbpt.so.  Fails loudly when it is missing: there is no fallback implementation."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = library_path()
+    if not os.path.exists(path):
+        raise BptError(f"{path} not found: build it with `make -C buas_pathtracer_b200/csrc` "
+                       "(or __graft_entry__.build()); there is no CPU/Python fallback")
+    L = C.CDLL(path)
+    vp, P = C.c_void_p, C.POINTER
+    L.bpt_last_error.restype = C.c_char_p
+    L.bpt_version.restype = C.c_char_p
+    L.bpt_make_displaced_icosphere.restype = C.c_uint32
+    L.bpt_make_displaced_icosphere.argtypes = [C.c_uint32, C.c_float, vp]
+    L.bpt_make_procedural_skydome.restype = C.c_int
+    L.bpt_make_procedural_skydome.argtypes = [C.c_uint32, C.c_uint32, vp]
+    L.bpt_create.restype = C.c_int
+    L.bpt_create.argtypes = [C.c_int, P(vp)]
+    L.bpt_destroy.restype = None
+    L.bpt_destroy.argtypes = [vp]
+    L.bpt_set_sampler_tables.restype = C.c_int
+    L.bpt_set_sampler_tables.argtypes = [vp, vp, vp, vp, vp]
+    for name in ("upload_scene", "update_settings"):
+        f = getattr(L, "bpt_" + name)
+        f.restype = C.c_int
+        f.argtypes = [vp, vp]
+    L.bpt_film_resize.restype = C.c_int
+    L.bpt_film_resize.argtypes = [vp, C.c_uint32, C.c_uint32]
+    L.bpt_film_clear.restype = C.c_int
+    L.bpt_film_clear.argtypes = [vp]
+    L.bpt_film_use_external.restype = C.c_int
+    L.bpt_film_use_external.argtypes = [vp, vp, C.c_uint32, C.c_uint32]
+    L.bpt_film_device_ptr.restype = C.c_int
+    L.bpt_film_device_ptr.argtypes = [vp, P(vp)]
+    L.bpt_download_film.restype = C.c_int
+    L.bpt_download_film.argtypes = [vp, vp]
+    L.bpt_render_pass.restype = C.c_int
+    L.bpt_render_pass.argtypes = [vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32]
+    L.bpt_sync.restype = C.c_int
+    L.bpt_sync.argtypes = [vp]
+    L.bpt_trace.restype = C.c_int
+    L.bpt_trace.argtypes = [vp, C.c_uint32, vp, C.c_int, C.c_uint32, vp]
+    L.bpt_set_sample_records.restype = C.c_int
+    L.bpt_set_sample_records.argtypes = [vp, vp, C.c_uint64]
+    L.bpt_stats_enable.restype = C.c_int
+    L.bpt_stats_enable.argtypes = [vp, C.c_int]
+    L.bpt_get_stats.restype = C.c_int
+    L.bpt_get_stats.argtypes = [vp, P(capi.Stats), C.c_int]
+    L.bpt_get_pass_timing.restype = C.c_int
+    L.bpt_get_pass_timing.argtypes = [vp, P(capi.PassTiming)]
+    _LIB = L
+    return L
+
+
+def _check(rc, what):
+    if rc != 0:
+        msg = load_library().bpt_last_error().decode(errors="replace")
+        raise BptError(f"{what} failed ({rc}): {msg}")
+
+
+def sampler_tables():
+    """The four sampler lookup tables as uint8 arrays (data file written by oracle/tools/dump_sampler_tables.py)."""
+    blob = np.fromfile(os.path.join(HERE, "data", "sampler_tables.bin"), dtype=np.uint8)
+    assert blob.size == 16384 + 65536 + 131072 + 131072
+    return blob[:16384], blob[16384:81920], blob[81920:212992], blob[212992:]
+
+
+class Scene(capi.HostScene):
+    """Host scene of the product library (mirrors Raytracer/scene.h:134-149)."""
+
+    def __init__(self):
+        super().__init__(load_library(), "bpt_")
+
+
+def make_displaced_icosphere(level, amplitude=0.08):
+    L = load_library()
+    n = L.bpt_make_displaced_icosphere(level, amplitude, None)
+    if n == 0:
+        raise BptError(L.bpt_last_error().decode())
+    tris = np.zeros((n, 9), np.float32)
+    L.bpt_make_displaced_icosphere(level, amplitude, tris.ctypes.data)
+    return tris
+
+
+def make_procedural_skydome(w=2048, h=1024):
+    L = load_library()
+    px = np.zeros((h, w, 3), np.float32)
+    _check(L.bpt_make_procedural_skydome(w, h, px.ctypes.data), "bpt_make_procedural_skydome")
+    return px
+
+
+class Renderer:
+    """One GPU context (one per process/GPU).  Raises BptError when no CUDA device is usable."""
+
+    def __init__(self, device=0):
+        self.lib = load_library()
+        h = C.c_void_p()
+        _check(self.lib.bpt_create(device, C.byref(h)), "bpt_create")
+        self.handle = h
+        self.device = device
+        self.w = self.h = 0
+        self._records = None
+        perm, sobol, scr, rank = sampler_tables()
+        _check(self.lib.bpt_set_sampler_tables(self.handle, perm.ctypes.data, sobol.ctypes.data, scr.ctypes.data,
+                                               rank.ctypes.data), "bpt_set_sampler_tables")
+
+    def close(self):
+        if getattr(self, "handle", None):
+            self.lib.bpt_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def upload_scene(self, scene):
+        _check(self.lib.bpt_upload_scene(self.handle, scene.handle), "bpt_upload_scene")
+
+    def update_settings(self, scene):
+        _check(self.lib.bpt_update_settings(self.handle, scene.handle), "bpt_update_settings")
+
+    def film_resize(self, w, h):
+        _check(self.lib.bpt_film_resize(self.handle, w, h), "bpt_film_resize")
+        self.w, self.h = w, h
+
+    def film_use_external(self, device_ptr, w, h):
+        _check(self.lib.bpt_film_use_external(self.handle, C.c_void_p(device_ptr), w, h), "bpt_film_use_external")
+        self.w, self.h = w, h
+
+    def film_clear(self):
+        _check(self.lib.bpt_film_clear(self.handle), "bpt_film_clear")
+
+    def render_pass(self, spp, rect=None, frame_count=0, salt=0):
+        x0, y0, x1, y1 = rect if rect else (0, 0, self.w, self.h)
+        _check(self.lib.bpt_render_pass(self.handle, x0, y0, x1, y1, frame_count, spp, 0, salt), "bpt_render_pass")
+
+    def sync(self):
+        _check(self.lib.bpt_sync(self.handle), "bpt_sync")
+
+    def download_film(self, out=None):
+        if out is None:
+            out = np.empty((self.h, self.w, 4), np.float32)
+        _check(self.lib.bpt_download_film(self.handle, out.ctypes.data), "bpt_download_film")
+        return out
+
+    def trace(self, rays, mode=capi.TRACE_CLOSEST, ignored_primitive=0):
+        rays = np.ascontiguousarray(rays, dtype=capi.RAY_DTYPE)
+        hits = np.zeros(rays.shape[0], dtype=capi.HIT_DTYPE)
+        _check(self.lib.bpt_trace(self.handle, rays.shape[0], rays.ctypes.data, mode, ignored_primitive,
+                                  hits.ctypes.data), "bpt_trace")
+        return hits
+
+    def attach_records(self, count):
+        if count:
+            self._records = np.zeros(count, dtype=capi.RECORD_DTYPE)
+            _check(self.lib.bpt_set_sample_records(self.handle, self._records.ctypes.data, count), "bpt_set_sample_records")
+        else:
+            self._records = None
+            _check(self.lib.bpt_set_sample_records(self.handle, None, 0), "bpt_set_sample_records")
+        return self._records
+
+    def stats_enable(self, on=True):
+        _check(self.lib.bpt_stats_enable(self.handle, int(on)), "bpt_stats_enable")
+
+    def get_stats(self, reset=False):
+        st = capi.Stats()
+        _check(self.lib.bpt_get_stats(self.handle, C.byref(st), int(reset)), "bpt_get_stats")
+        return st
+
+    def pass_timing(self):
+        t = capi.PassTiming()
+        _check(self.lib.bpt_get_pass_timing(self.handle, C.byref(t)), "bpt_get_pass_timing")
+        return t
