@@ -79,7 +79,10 @@ SAMPLING_UNIFORM, SAMPLING_BLUE_NOISE, SAMPLING_STRATIFIED = 0, 1, 2
 class Stats(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in (
         "rays", "shadow_rays", "tlas_node_pops", "instances_visited", "mesh_intersection_count",
-        "mesh_bvh_traversals", "mesh_node_traversals", "mesh_leaf_traversals", "triangles_tested", "samples")]
+        "mesh_bvh_traversals", "mesh_node_traversals", "mesh_leaf_traversals", "triangles_tested", "samples",
+        "shadow_tlas_node_pops", "shadow_instances_visited", "shadow_mesh_intersection_count",
+        "shadow_mesh_bvh_traversals", "shadow_mesh_node_traversals", "shadow_mesh_leaf_traversals",
+        "shadow_triangles_tested")]
 
     def as_dict(self):
         return {n: int(getattr(self, n)) for n, _ in self._fields_}

@@ -62,6 +62,8 @@ struct bpt_ctx {
     bool pass_recorded = false;
     uint32_t launches = 0, trace_launches = 0;
     uint64_t total_launches = 0;
+    uint64_t h2d_bytes = 0, d2h_bytes = 0;
+    uint64_t samples = 0;
 };
 
 namespace {
@@ -74,6 +76,7 @@ int upload(bpt_ctx* ctx, const T* host, size_t count, const T** out, std::vector
     CK(cudaMalloc(&d, bytes));
     owner->push_back(d);
     if (count) CK(cudaMemcpyAsync(d, host, count*sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+    ctx->h2d_bytes += count*sizeof(T);
     *out = (const T*)d;
     return BPT_OK;
 }
@@ -228,6 +231,7 @@ int bpt_update_settings(bpt_ctx* ctx, const bpt_scene* scene) {
     CK(cudaSetDevice(ctx->device));
     latch_settings(ctx, scene);
     CK(cudaMemcpyAsync(ctx->d_filter, scene->filter.cache, 512*sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    ctx->h2d_bytes += 512*sizeof(float) + sizeof(bpt_camera) + sizeof(bpt_settings);
     CK(cudaStreamSynchronize(ctx->stream));
     ctx->sc.filter_lut = ctx->d_filter;
     return BPT_OK;
@@ -392,6 +396,7 @@ int bpt_download_film(bpt_ctx* ctx, float* out) {
     CK(cudaSetDevice(ctx->device));
     CK(cudaMemcpyAsync(out, ctx->film, (size_t)ctx->film_w*ctx->film_h*sizeof(float4), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
+    ctx->d2h_bytes += (uint64_t)ctx->film_w*ctx->film_h*sizeof(float4);
     return BPT_OK;
 }
 
@@ -417,8 +422,12 @@ int bpt_get_stats(bpt_ctx* ctx, bpt_stats* out, int reset) {
     CK(cudaMemcpy(&h, ctx->d_stats, sizeof(h), cudaMemcpyDeviceToHost));
     out->rays = h.v[0]; out->shadow_rays = h.v[1]; out->tlas_node_pops = h.v[2]; out->instances_visited = h.v[3];
     out->mesh_intersection_count = h.v[4]; out->mesh_bvh_traversals = h.v[5]; out->mesh_node_traversals = h.v[6];
-    out->mesh_leaf_traversals = h.v[7]; out->triangles_tested = h.v[8]; out->samples = h.v[9];
-    if (reset) CK(cudaMemset(ctx->d_stats, 0, sizeof(DStats)));
+    out->mesh_leaf_traversals = h.v[7]; out->triangles_tested = h.v[8]; out->samples = ctx->samples;
+    out->shadow_tlas_node_pops = h.v[10]; out->shadow_instances_visited = h.v[11];
+    out->shadow_mesh_intersection_count = h.v[12]; out->shadow_mesh_bvh_traversals = h.v[13];
+    out->shadow_mesh_node_traversals = h.v[14]; out->shadow_mesh_leaf_traversals = h.v[15];
+    out->shadow_triangles_tested = h.v[16];
+    if (reset) { CK(cudaMemset(ctx->d_stats, 0, sizeof(DStats))); ctx->samples = 0; }
     return BPT_OK;
 }
 
@@ -439,6 +448,7 @@ int bpt_trace(bpt_ctx* ctx, uint32_t n, const bpt_ray* rays, int mode, uint32_t 
     CK(cudaMalloc((void**)&d_rays, (size_t)n*sizeof(bpt_ray)));
     CK(cudaMalloc((void**)&d_hits, (size_t)n*sizeof(bpt_hit)));
     CK(cudaMemcpyAsync(d_rays, rays, (size_t)n*sizeof(bpt_ray), cudaMemcpyHostToDevice, ctx->stream));
+    ctx->h2d_bytes += (uint64_t)n*sizeof(bpt_ray); ctx->d2h_bytes += (uint64_t)n*sizeof(bpt_hit);
     uint32_t grid = grid_for(ctx, n, 128, 16);
     bool st = ctx->stats_enabled;
     if (mode == BPT_TRACE_CLOSEST) {
@@ -542,7 +552,7 @@ int bpt_render_pass(bpt_ctx* ctx, int32_t x0, int32_t y0, int32_t x1, int32_t y1
 
                 begin_span(ctx, ST_SHADE);
                 k_shade<<<grid_for(ctx, work, 128, 16), 128, 0, s>>>(sc, ctx->st, b, bounce, in_queue, in_count, b.slots,
-                                                                    ctx->q.active[out], counters + out, ctx->q.shadow, counters + 2);
+                                                                    ctx->q.active[out], counters + out, ctx->q.shadow, counters + 2, ctx->d_stats);
                 end_span(ctx);
                 ctx->launches++;
 
@@ -570,12 +580,14 @@ int bpt_render_pass(bpt_ctx* ctx, int32_t x0, int32_t y0, int32_t x1, int32_t y1
                 CK(cudaMemcpyAsync(ctx->host_records + first, ctx->d_records, (size_t)b.slots*sizeof(bpt_sample_record),
                                    cudaMemcpyDeviceToHost, s));
                 CK(cudaStreamSynchronize(s));
+                ctx->d2h_bytes += (uint64_t)b.slots*sizeof(bpt_sample_record);
             }
         }
     }
     CK(cudaEventRecord(ctx->pass_end, s));
     ctx->pass_recorded = true;
     ctx->total_launches += ctx->launches;
+    ctx->samples += total_samples;
     CK(cudaGetLastError());
     return BPT_OK;
 }
@@ -595,6 +607,20 @@ int bpt_get_pass_timing(bpt_ctx* ctx, bpt_pass_timing* out) {
     out->raygen_ms = acc[ST_RAYGEN]; out->trace_ms = acc[ST_TRACE]; out->shade_ms = acc[ST_SHADE];
     out->shadow_ms = acc[ST_SHADOW]; out->splat_ms = acc[ST_SPLAT];
     out->kernel_launches = ctx->launches; out->trace_launches = ctx->trace_launches;
+    return BPT_OK;
+}
+
+int bpt_set_detailed_timing(bpt_ctx* ctx, int enable) {
+    if (!ctx) return BPT_ERR_ARG;
+    ctx->detailed_timing = enable != 0;
+    return BPT_OK;
+}
+
+int bpt_get_transfer_bytes(bpt_ctx* ctx, uint64_t* h2d, uint64_t* d2h, int reset) {
+    if (!ctx) return BPT_ERR_ARG;
+    if (h2d) *h2d = ctx->h2d_bytes;
+    if (d2h) *d2h = ctx->d2h_bytes;
+    if (reset) { ctx->h2d_bytes = 0; ctx->d2h_bytes = 0; }
     return BPT_OK;
 }
 

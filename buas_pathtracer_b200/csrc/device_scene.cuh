@@ -114,7 +114,7 @@ struct DQueues {
 };
 
 struct DStats {             // device mirror of bpt_stats
-    unsigned long long v[10];
+    unsigned long long v[20];   // [0..9] totals as in bpt_stats, [10..16] shadow-only traversal counters
 };
 
 } // namespace bpt

@@ -259,15 +259,27 @@ k_raygen(DScene sc, DPathState st, BatchDesc b) {
     }
 }
 
-BPT_D void flush_counters(DStats* stats, const TraceCounters& c, uint32_t rays, uint32_t shadow) {
-    // warp-aggregate, then one atomic per counter per warp
-    unsigned long long vals[9] = {rays, shadow, c.tlas_pops, c.instances, c.mesh_calls, c.blas_pops, c.blas_inner, c.blas_leaves, c.tris};
+BPT_D void flush_counters(DStats* stats, const TraceCounters& c, bool shadow) {
+    // warp-aggregate, then one atomic per counter per warp (rays themselves are counted in k_shade / k_trace_api)
+    unsigned long long vals[7] = {c.tlas_pops, c.instances, c.mesh_calls, c.blas_pops, c.blas_inner, c.blas_leaves, c.tris};
     #pragma unroll
-    for (int k = 0; k < 9; ++k) {
+    for (int k = 0; k < 7; ++k) {
         unsigned long long v = vals[k];
         #pragma unroll
         for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
-        if ((threadIdx.x & 31) == 0 && v) atomicAdd(&stats->v[k], v);
+        if ((threadIdx.x & 31) == 0 && v) {
+            atomicAdd(&stats->v[2 + k], v);
+            if (shadow) atomicAdd(&stats->v[10 + k], v);
+        }
+    }
+}
+
+BPT_D void flush_ray_counts(DStats* stats, uint32_t rays, uint32_t shadow) {
+    rays = __reduce_add_sync(0xFFFFFFFFu, rays);
+    shadow = __reduce_add_sync(0xFFFFFFFFu, shadow);
+    if ((threadIdx.x & 31) == 0) {
+        if (rays) atomicAdd(&stats->v[0], (unsigned long long)rays);
+        if (shadow) atomicAdd(&stats->v[1], (unsigned long long)shadow);
     }
 }
 
@@ -278,7 +290,6 @@ k_trace_closest(DScene sc, DPathState st, const uint32_t* __restrict__ in_queue,
                 uint32_t n_fixed, DStats* stats) {
     uint32_t n = n_ptr ? *n_ptr : n_fixed;
     TraceCounters ctr = {};
-    uint32_t rays = 0;
     uint32_t stride = gridDim.x*blockDim.x;
     uint32_t base = blockIdx.x*blockDim.x + threadIdx.x;
     // whole warps iterate together so the stats shuffle stays converged
@@ -291,10 +302,9 @@ k_trace_closest(DScene sc, DPathState st, const uint32_t* __restrict__ in_queue,
             trace_ray<false, STATS>(sc, v3(o), v3(d), o.w, 0u, h, ctr);
             st.hit[slot] = make_float4(h.t, __uint_as_float(h.prim), __uint_as_float(h.tri), h.v);
             st.hit_w[slot] = h.w;
-            rays += 1;
         }
     }
-    if (STATS) flush_counters(stats, ctr, rays, 0);
+    if (STATS) flush_counters(stats, ctr, false);
 }
 
 // intersect_shadow_ray for every queued NEE sample (integrators.cpp:756); unoccluded -> add the pending contribution
@@ -303,7 +313,6 @@ __global__ void __launch_bounds__(128)
 k_trace_shadow(DScene sc, DPathState st, const DShadowItem* __restrict__ items, const uint32_t* __restrict__ n_ptr, DStats* stats) {
     uint32_t n = *n_ptr;
     TraceCounters ctr = {};
-    uint32_t rays = 0;
     uint32_t stride = gridDim.x*blockDim.x;
     uint32_t base = blockIdx.x*blockDim.x + threadIdx.x;
     for (uint32_t i0 = base - (threadIdx.x & 31); i0 < n; i0 += stride) {
@@ -312,7 +321,6 @@ k_trace_shadow(DScene sc, DPathState st, const DShadowItem* __restrict__ items, 
             float4 o = items[i].o_maxt, d = items[i].d_light, c = items[i].contrib_slot;
             HitRecord h;
             trace_ray<true, STATS>(sc, v3(o), v3(d), o.w, __float_as_uint(d.w), h, ctr);
-            rays += 1;
             if (h.prim == BPT_HIT_MISS) {
                 uint32_t slot = __float_as_uint(c.w);
                 float4 r = st.radiance[slot];
@@ -321,7 +329,7 @@ k_trace_shadow(DScene sc, DPathState st, const DShadowItem* __restrict__ items, 
             }
         }
     }
-    if (STATS) flush_counters(stats, ctr, rays, rays);
+    if (STATS) flush_counters(stats, ctr, true);
 }
 
 // warp-aggregated append: returns this lane's index in the destination queue
@@ -341,8 +349,9 @@ __global__ void __launch_bounds__(128)
 k_shade(DScene sc, DPathState st, BatchDesc b, uint32_t bounce,
         const uint32_t* __restrict__ in_queue, const uint32_t* __restrict__ n_ptr, uint32_t n_fixed,
         uint32_t* __restrict__ out_queue, uint32_t* out_count,
-        DShadowItem* __restrict__ shadow_items, uint32_t* shadow_count) {
+        DShadowItem* __restrict__ shadow_items, uint32_t* shadow_count, DStats* stats) {
     uint32_t n = n_ptr ? *n_ptr : n_fixed;
+    uint32_t n_rays = 0, n_shadow = 0;
     uint32_t stride = gridDim.x*blockDim.x;
     uint32_t base = blockIdx.x*blockDim.x + threadIdx.x;
     const bpt_settings& set = sc.settings;
@@ -579,7 +588,10 @@ k_shade(DScene sc, DPathState st, BatchDesc b, uint32_t bounce,
         if (alive) out_queue[qi] = slot;
         uint32_t si = queue_append(shadow_count, want_shadow);
         if (want_shadow) shadow_items[si] = sh;
+        n_rays += (i < n ? 1u : 0u) + (want_shadow ? 1u : 0u);
+        n_shadow += want_shadow ? 1u : 0u;
     }
+    flush_ray_counts(stats, n_rays, n_shadow);
 }
 
 // render_tile's tail (raytracer.cpp:469-488) + splat_filter (:187-259): one thread per pixel of the batch walks that
@@ -711,7 +723,8 @@ k_trace_api(DScene sc, const bpt_ray* __restrict__ rays, uint32_t n, uint32_t ig
             out[i] = res;
         }
     }
-    if (STATS) flush_counters(stats, ctr, cnt, OCC ? cnt : 0);
+    if (STATS) flush_counters(stats, ctr, OCC);
+    flush_ray_counts(stats, cnt, OCC ? cnt : 0);
 }
 
 __global__ void k_reset_counters(uint32_t* counters, int which_mask) {

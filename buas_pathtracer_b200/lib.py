@@ -14,7 +14,7 @@ _LIB = None
 DEVICE_SYMBOLS = [
     "create", "destroy", "set_sampler_tables", "upload_scene", "update_settings", "film_resize", "film_clear",
     "film_use_external", "film_device_ptr", "download_film", "render_pass", "sync", "trace", "set_sample_records",
-    "stats_enable", "get_stats", "get_pass_timing",
+    "stats_enable", "get_stats", "get_pass_timing", "set_detailed_timing", "get_transfer_bytes",
 ]
 MISC_SYMBOLS = ["last_error", "version", "make_displaced_icosphere", "make_procedural_skydome"]
 
@@ -87,6 +87,10 @@ def load_library():
     L.bpt_get_stats.argtypes = [vp, P(capi.Stats), C.c_int]
     L.bpt_get_pass_timing.restype = C.c_int
     L.bpt_get_pass_timing.argtypes = [vp, P(capi.PassTiming)]
+    L.bpt_set_detailed_timing.restype = C.c_int
+    L.bpt_set_detailed_timing.argtypes = [vp, C.c_int]
+    L.bpt_get_transfer_bytes.restype = C.c_int
+    L.bpt_get_transfer_bytes.argtypes = [vp, P(C.c_uint64), P(C.c_uint64), C.c_int]
     _LIB = L
     return L
 
@@ -207,6 +211,14 @@ class Renderer:
         st = capi.Stats()
         _check(self.lib.bpt_get_stats(self.handle, C.byref(st), int(reset)), "bpt_get_stats")
         return st
+
+    def set_detailed_timing(self, on=True):
+        _check(self.lib.bpt_set_detailed_timing(self.handle, int(on)), "bpt_set_detailed_timing")
+
+    def transfer_bytes(self, reset=False):
+        a, b = C.c_uint64(), C.c_uint64()
+        _check(self.lib.bpt_get_transfer_bytes(self.handle, C.byref(a), C.byref(b), int(reset)), "bpt_get_transfer_bytes")
+        return a.value, b.value
 
     def pass_timing(self):
         t = capi.PassTiming()

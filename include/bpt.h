@@ -157,6 +157,10 @@ typedef struct bpt_stats {
     uint64_t mesh_leaf_traversals;    /* g_stats.mesh_leaf_traversals */
     uint64_t triangles_tested;
     uint64_t samples;                 /* integrator invocations */
+    /* the same traversal counters restricted to shadow rays (so closest-hit = total - shadow) */
+    uint64_t shadow_tlas_node_pops, shadow_instances_visited, shadow_mesh_intersection_count,
+             shadow_mesh_bvh_traversals, shadow_mesh_node_traversals, shadow_mesh_leaf_traversals,
+             shadow_triangles_tested;
 } bpt_stats;
 
 /* Per-sample record for parity tests (bpt_render_pass with a record buffer attached). */
@@ -286,7 +290,8 @@ BPT_API int bpt_trace(bpt_ctx* ctx, uint32_t n, const bpt_ray* rays, int mode, u
 /* Attach a host buffer of (x1-x0)*(y1-y0)*spp records, filled (pixel-major, sample-minor) by the next
  * bpt_render_pass; NULL detaches. */
 BPT_API int bpt_set_sample_records(bpt_ctx* ctx, bpt_sample_record* host_records, uint64_t capacity);
-BPT_API int bpt_stats_enable(bpt_ctx* ctx, int enable);     /* counting kernels are separate instantiations */
+/* rays / shadow_rays / samples are always counted; the traversal counters need the counting instantiations. */
+BPT_API int bpt_stats_enable(bpt_ctx* ctx, int enable);
 BPT_API int bpt_get_stats(bpt_ctx* ctx, bpt_stats* out, int reset);
 /* GPU time of the last render pass by stage, measured with CUDA events on the context's stream (ms). */
 typedef struct bpt_pass_timing {
@@ -295,6 +300,10 @@ typedef struct bpt_pass_timing {
     uint32_t trace_launches;
 } bpt_pass_timing;
 BPT_API int bpt_get_pass_timing(bpt_ctx* ctx, bpt_pass_timing* out);
+/* per-stage CUDA-event timing (two event records around every kernel); off by default */
+BPT_API int bpt_set_detailed_timing(bpt_ctx* ctx, int enable);
+/* cumulative bytes this context copied host->device / device->host (scene uploads, rays, film, records) */
+BPT_API int bpt_get_transfer_bytes(bpt_ctx* ctx, uint64_t* h2d, uint64_t* d2h, int reset);
 
 #ifdef __cplusplus
 }
