@@ -2,6 +2,7 @@
 // schedule, diagnostics.  There is no CPU fallback anywhere in this file: without a usable CUDA device every entry
 // point fails with BPT_ERR_CUDA.
 #include <cuda_runtime.h>
+#include <math.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -27,6 +28,8 @@ struct TimedSpan { cudaEvent_t a, b; int stage; };
 struct bpt_ctx {
     int device = 0;
     int sm_count = 148;
+    uint32_t refill = 8;                  // persistent warps fetch new rays once this many lanes are idle (or idle is the largest group)
+    int trace_ctas_per_sm = 8;            // resident CTAs of the persistent traversal kernels (occupancy query)
     cudaStream_t stream = nullptr;
 
     DScene sc{};
@@ -184,6 +187,15 @@ int bpt_create(int device, bpt_ctx** out_ctx) {
     CK(cudaMalloc((void**)&ctx->d_filter, 512*sizeof(float)));
     CK(cudaEventCreate(&ctx->pass_begin));
     CK(cudaEventCreate(&ctx->pass_end));
+    {
+        int a = 0, b = 0;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, k_trace_closest<false>, 128, 0);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_trace_shadow<false>, 128, 0);
+        int m = std::min(a, b);
+        if (m > 0) ctx->trace_ctas_per_sm = m;
+    }
+    if (const char* e = getenv("BPT_REFILL")) { int v = atoi(e); if (v >= 1 && v <= 33) ctx->refill = (uint32_t)v; }
+    if (const char* e = getenv("BPT_TRACE_CTAS")) { int v = atoi(e); if (v >= 1 && v <= 32) ctx->trace_ctas_per_sm = v; }
     const char* dt = getenv("BPT_DETAILED_TIMING");
     ctx->detailed_timing = dt && atoi(dt) != 0;
     *out_ctx = ctx;
@@ -313,6 +325,22 @@ int bpt_upload_scene(bpt_ctx* ctx, const bpt_scene* scene) {
     for (uint32_t l : scene->lights) {
         if (l >= scene->primitives.size()) { set_error("bpt_upload_scene: light id %u is not a primitive (emissive plane?)", l); return BPT_ERR_UNSUPPORTED; }
     }
+
+    // FMNMX slab test precondition (trace.cuh make_ray): all node boxes finite and inside 1e15
+    bool tame = true;
+    auto check_nodes = [&](const std::vector<bpt_bvh_node>& nodes) {
+        for (const bpt_bvh_node& nd : nodes)
+            for (int k = 0; k < 3; ++k) {
+                float ext = fabsf(nd.bv_p[k]) + fabsf(nd.bv_r[k]);
+                if (!(ext < 1e15f)) {
+                    // the empty-scene root has bv_r = -inf by construction (it can never be hit); anything else disables the fast path
+                    tame = false;
+                }
+            }
+    };
+    check_nodes(scene->tlas.nodes);
+    check_nodes(blas_nodes);
+    sc.tame_bounds = tame ? 1u : 0u;
 
     int rc = 0;
     const bpt_bvh_node* d_tlas = nullptr; const bpt_bvh_node* d_blas = nullptr;
@@ -449,20 +477,23 @@ int bpt_trace(bpt_ctx* ctx, uint32_t n, const bpt_ray* rays, int mode, uint32_t 
     CK(cudaMalloc((void**)&d_hits, (size_t)n*sizeof(bpt_hit)));
     CK(cudaMemcpyAsync(d_rays, rays, (size_t)n*sizeof(bpt_ray), cudaMemcpyHostToDevice, ctx->stream));
     ctx->h2d_bytes += (uint64_t)n*sizeof(bpt_ray); ctx->d2h_bytes += (uint64_t)n*sizeof(bpt_hit);
-    uint32_t grid = grid_for(ctx, n, 128, 16);
+    uint32_t* d_cursor = nullptr;
+    CK(cudaMalloc((void**)&d_cursor, 256));
+    CK(cudaMemsetAsync(d_cursor, 0, 256, ctx->stream));
+    uint32_t grid = grid_for(ctx, n, 128, ctx->trace_ctas_per_sm);
     bool st = ctx->stats_enabled;
     if (mode == BPT_TRACE_CLOSEST) {
-        if (st) k_trace_api<false, true ><<<grid, 128, 0, ctx->stream>>>(ctx->sc, d_rays, n, ignored, d_hits, ctx->tri_original, ctx->d_stats);
-        else    k_trace_api<false, false><<<grid, 128, 0, ctx->stream>>>(ctx->sc, d_rays, n, ignored, d_hits, ctx->tri_original, ctx->d_stats);
+        if (st) k_trace_api<false, true ><<<grid, 128, 0, ctx->stream>>>(ctx->sc, d_rays, n, ignored, d_hits, ctx->tri_original, d_cursor, ctx->refill, ctx->d_stats);
+        else    k_trace_api<false, false><<<grid, 128, 0, ctx->stream>>>(ctx->sc, d_rays, n, ignored, d_hits, ctx->tri_original, d_cursor, ctx->refill, ctx->d_stats);
     } else {
-        if (st) k_trace_api<true, true ><<<grid, 128, 0, ctx->stream>>>(ctx->sc, d_rays, n, ignored, d_hits, ctx->tri_original, ctx->d_stats);
-        else    k_trace_api<true, false><<<grid, 128, 0, ctx->stream>>>(ctx->sc, d_rays, n, ignored, d_hits, ctx->tri_original, ctx->d_stats);
+        if (st) k_trace_api<true, true ><<<grid, 128, 0, ctx->stream>>>(ctx->sc, d_rays, n, ignored, d_hits, ctx->tri_original, d_cursor, ctx->refill, ctx->d_stats);
+        else    k_trace_api<true, false><<<grid, 128, 0, ctx->stream>>>(ctx->sc, d_rays, n, ignored, d_hits, ctx->tri_original, d_cursor, ctx->refill, ctx->d_stats);
     }
     ctx->total_launches += 1;
     cudaError_t e = cudaGetLastError();
     if (e == cudaSuccess) e = cudaMemcpyAsync(out, d_hits, (size_t)n*sizeof(bpt_hit), cudaMemcpyDeviceToHost, ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-    cudaFree(d_rays); cudaFree(d_hits);
+    cudaFree(d_rays); cudaFree(d_hits); cudaFree(d_cursor);
     if (e != cudaSuccess) { set_error("bpt_trace: %s", cudaGetErrorString(e)); return BPT_ERR_CUDA; }
     return BPT_OK;
 }
@@ -539,14 +570,14 @@ int bpt_render_pass(bpt_ctx* ctx, int32_t x0, int32_t y0, int32_t x1, int32_t y1
                 // counters: [in] = active count for this bounce (bounce 0 uses the identity queue), [out] and [2] (shadow) reset
                 const uint32_t* in_queue = bounce == 0 ? nullptr : ctx->q.active[in];
                 const uint32_t* in_count = bounce == 0 ? nullptr : counters + in;
-                k_reset_counters<<<1, 32, 0, s>>>(counters, (1 << out) | (1 << 2));
+                k_reset_counters<<<1, 32, 0, s>>>(counters, (1 << out) | (1 << 2) | (1 << 3) | (1 << 4));
                 ctx->launches++;
                 uint32_t work = b.slots;    // upper bound; kernels read the true count on the device
 
                 begin_span(ctx, ST_TRACE);
-                uint32_t tg = grid_for(ctx, work, 128, 16);
-                if (stats) k_trace_closest<true ><<<tg, 128, 0, s>>>(sc, ctx->st, in_queue, in_count, b.slots, ctx->d_stats);
-                else       k_trace_closest<false><<<tg, 128, 0, s>>>(sc, ctx->st, in_queue, in_count, b.slots, ctx->d_stats);
+                uint32_t tg = grid_for(ctx, work, 128, ctx->trace_ctas_per_sm);
+                if (stats) k_trace_closest<true ><<<tg, 128, 0, s>>>(sc, ctx->st, in_queue, in_count, b.slots, counters + 3, ctx->refill, ctx->d_stats);
+                else       k_trace_closest<false><<<tg, 128, 0, s>>>(sc, ctx->st, in_queue, in_count, b.slots, counters + 3, ctx->refill, ctx->d_stats);
                 end_span(ctx);
                 ctx->launches++; ctx->trace_launches++;
 
@@ -557,8 +588,8 @@ int bpt_render_pass(bpt_ctx* ctx, int32_t x0, int32_t y0, int32_t x1, int32_t y1
                 ctx->launches++;
 
                 begin_span(ctx, ST_SHADOW);
-                if (stats) k_trace_shadow<true ><<<tg, 128, 0, s>>>(sc, ctx->st, ctx->q.shadow, counters + 2, ctx->d_stats);
-                else       k_trace_shadow<false><<<tg, 128, 0, s>>>(sc, ctx->st, ctx->q.shadow, counters + 2, ctx->d_stats);
+                if (stats) k_trace_shadow<true ><<<tg, 128, 0, s>>>(sc, ctx->st, ctx->q.shadow, counters + 2, counters + 4, ctx->refill, ctx->d_stats);
+                else       k_trace_shadow<false><<<tg, 128, 0, s>>>(sc, ctx->st, ctx->q.shadow, counters + 2, counters + 4, ctx->refill, ctx->d_stats);
                 end_span(ctx);
                 ctx->launches++; ctx->trace_launches++;
             }

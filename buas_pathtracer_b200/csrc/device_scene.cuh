@@ -80,6 +80,7 @@ struct DScene {
     uint32_t filter_radius;            // FilterCache::kernel_size
     uint32_t filter_lut_size;          // FilterCache::cache_size (0 = Box)
     uint32_t film_w, film_h;
+    uint32_t tame_bounds;              // every TLAS/BLAS node box lies inside |x| < 1e15 (enables the FMNMX slab test)
 };
 
 // ---- wavefront path state (SoA, one entry per path slot of the current batch) ------------------------------------

@@ -283,52 +283,60 @@ BPT_D void flush_ray_counts(DStats* stats, uint32_t rays, uint32_t shadow) {
     }
 }
 
+struct ClosestSrc {        // rays come from the path state (through the active queue), hits go back to it
+    DPathState st;
+    const uint32_t* queue;
+    BPT_D void load(uint32_t i, V3& o, V3& d, float& max_t, uint32_t& ignored) const {
+        uint32_t slot = queue ? queue[i] : i;
+        float4 ro = st.ray_o[slot], rd = st.ray_d[slot];
+        o = v3(ro); d = v3(rd); max_t = ro.w; ignored = 0u;       // intersect_scene passes PrimitiveID 0 (intersection.cpp:608)
+    }
+    BPT_D void store(uint32_t i, const HitRecord& h) const {
+        uint32_t slot = queue ? queue[i] : i;
+        st.hit[slot] = make_float4(h.t, __uint_as_float(h.prim), __uint_as_float(h.tri), h.v);
+        st.hit_w[slot] = h.w;
+    }
+};
+
+struct ShadowSrc {         // NEE shadow rays; an unoccluded ray releases its pending contribution (integrators.cpp:756-769)
+    DPathState st;
+    const DShadowItem* items;
+    BPT_D void load(uint32_t i, V3& o, V3& d, float& max_t, uint32_t& ignored) const {
+        float4 ro = items[i].o_maxt, rd = items[i].d_light;
+        o = v3(ro); d = v3(rd); max_t = ro.w; ignored = __float_as_uint(rd.w);
+    }
+    BPT_D void store(uint32_t i, const HitRecord& h) const {
+        if (h.prim == BPT_HIT_MISS) {
+            float4 c = items[i].contrib_slot;
+            uint32_t slot = __float_as_uint(c.w);
+            float4 r = st.radiance[slot];
+            r.x = r.x + c.x; r.y = r.y + c.y; r.z = r.z + c.z;
+            st.radiance[slot] = r;
+        }
+    }
+};
+
 // intersect_scene for every active path (integrators.cpp:615).  in_queue == nullptr means "slot = i".
 template <bool STATS>
 __global__ void __launch_bounds__(128)
 k_trace_closest(DScene sc, DPathState st, const uint32_t* __restrict__ in_queue, const uint32_t* __restrict__ n_ptr,
-                uint32_t n_fixed, DStats* stats) {
+                uint32_t n_fixed, uint32_t* cursor, uint32_t refill, DStats* stats) {
     uint32_t n = n_ptr ? *n_ptr : n_fixed;
     TraceCounters ctr = {};
-    uint32_t stride = gridDim.x*blockDim.x;
-    uint32_t base = blockIdx.x*blockDim.x + threadIdx.x;
-    // whole warps iterate together so the stats shuffle stays converged
-    for (uint32_t i0 = base - (threadIdx.x & 31); i0 < n; i0 += stride) {
-        uint32_t i = i0 + (threadIdx.x & 31);
-        if (i < n) {
-            uint32_t slot = in_queue ? in_queue[i] : i;
-            float4 o = st.ray_o[slot], d = st.ray_d[slot];
-            HitRecord h;
-            trace_ray<false, STATS>(sc, v3(o), v3(d), o.w, 0u, h, ctr);
-            st.hit[slot] = make_float4(h.t, __uint_as_float(h.prim), __uint_as_float(h.tri), h.v);
-            st.hit_w[slot] = h.w;
-        }
-    }
+    ClosestSrc src = {st, in_queue};
+    persistent_trace<false, STATS>(sc, src, n, cursor, refill, ctr);
     if (STATS) flush_counters(stats, ctr, false);
 }
 
-// intersect_shadow_ray for every queued NEE sample (integrators.cpp:756); unoccluded -> add the pending contribution
+// intersect_shadow_ray for every queued NEE sample (integrators.cpp:756)
 template <bool STATS>
 __global__ void __launch_bounds__(128)
-k_trace_shadow(DScene sc, DPathState st, const DShadowItem* __restrict__ items, const uint32_t* __restrict__ n_ptr, DStats* stats) {
+k_trace_shadow(DScene sc, DPathState st, const DShadowItem* __restrict__ items, const uint32_t* __restrict__ n_ptr,
+               uint32_t* cursor, uint32_t refill, DStats* stats) {
     uint32_t n = *n_ptr;
     TraceCounters ctr = {};
-    uint32_t stride = gridDim.x*blockDim.x;
-    uint32_t base = blockIdx.x*blockDim.x + threadIdx.x;
-    for (uint32_t i0 = base - (threadIdx.x & 31); i0 < n; i0 += stride) {
-        uint32_t i = i0 + (threadIdx.x & 31);
-        if (i < n) {
-            float4 o = items[i].o_maxt, d = items[i].d_light, c = items[i].contrib_slot;
-            HitRecord h;
-            trace_ray<true, STATS>(sc, v3(o), v3(d), o.w, __float_as_uint(d.w), h, ctr);
-            if (h.prim == BPT_HIT_MISS) {
-                uint32_t slot = __float_as_uint(c.w);
-                float4 r = st.radiance[slot];
-                r.x = r.x + c.x; r.y = r.y + c.y; r.z = r.z + c.z;
-                st.radiance[slot] = r;
-            }
-        }
-    }
+    ShadowSrc src = {st, items};
+    persistent_trace<true, STATS>(sc, src, n, cursor, refill, ctr);
     if (STATS) flush_counters(stats, ctr, true);
 }
 
@@ -688,43 +696,51 @@ __global__ void k_write_records(DPathState st, BatchDesc b, bpt_sample_record* _
     }
 }
 
-// bpt_trace: host ray batch -> bpt_hit (diagnostics / parity), closest or occlusion
+// bpt_trace: host ray batch -> bpt_hit (diagnostics / parity), closest or occlusion, through the same persistent loop
+template <bool OCC>
+struct ApiSrc {
+    DScene sc;
+    const bpt_ray* rays;
+    bpt_hit* out;
+    const uint32_t* tri_original;
+    uint32_t ignored;
+    BPT_D void load(uint32_t i, V3& o, V3& d, float& max_t, uint32_t& ign) const {
+        bpt_ray r = rays[i];
+        o = v3(r.o); d = v3(r.d); max_t = r.max_t; ign = OCC ? ignored : 0u;
+    }
+    BPT_D void store(uint32_t i, const HitRecord& h) const {
+        bpt_ray r = rays[i];
+        bpt_hit res;
+        res.t = OCC ? r.max_t : h.t;
+        res.primitive = h.prim;
+        res.triangle = 0xFFFFFFFFu;
+        res.n[0] = res.n[1] = res.n[2] = 0.0f;
+        res.p[0] = res.p[1] = res.p[2] = 0.0f;
+        if (!OCC && h.prim != BPT_HIT_MISS) {
+            V3 I, N; uint32_t mat;
+            hit_geometry(sc, v3(r.o), v3(r.d), h, I, N, mat);
+            res.n[0] = N.x; res.n[1] = N.y; res.n[2] = N.z;
+            res.p[0] = I.x; res.p[1] = I.y; res.p[2] = I.z;
+            if (h.tri != 0xFFFFFFFFu && !(h.prim & BPT_HIT_PLANE) && sc.primitives[h.prim].type == BPT_PRIM_MESH) {
+                res.triangle = tri_original[h.tri];
+            }
+        }
+        out[i] = res;
+    }
+};
+
 template <bool OCC, bool STATS>
 __global__ void __launch_bounds__(128)
 k_trace_api(DScene sc, const bpt_ray* __restrict__ rays, uint32_t n, uint32_t ignored, bpt_hit* __restrict__ out,
-            const uint32_t* __restrict__ tri_original, DStats* stats) {
+            const uint32_t* __restrict__ tri_original, uint32_t* cursor, uint32_t refill, DStats* stats) {
     TraceCounters ctr = {};
-    uint32_t cnt = 0;
-    uint32_t stride = gridDim.x*blockDim.x;
-    uint32_t base = blockIdx.x*blockDim.x + threadIdx.x;
-    for (uint32_t i0 = base - (threadIdx.x & 31); i0 < n; i0 += stride) {
-        uint32_t i = i0 + (threadIdx.x & 31);
-        if (i < n) {
-            bpt_ray r = rays[i];
-            V3 o = v3(r.o), d = v3(r.d);
-            HitRecord h;
-            trace_ray<OCC, STATS>(sc, o, d, r.max_t, OCC ? ignored : 0u, h, ctr);
-            cnt += 1;
-            bpt_hit res;
-            res.t = OCC ? r.max_t : h.t;
-            res.primitive = h.prim;
-            res.triangle = 0xFFFFFFFFu;
-            res.n[0] = res.n[1] = res.n[2] = 0.0f;
-            res.p[0] = res.p[1] = res.p[2] = 0.0f;
-            if (!OCC && h.prim != BPT_HIT_MISS) {
-                V3 I, N; uint32_t mat;
-                hit_geometry(sc, o, d, h, I, N, mat);
-                res.n[0] = N.x; res.n[1] = N.y; res.n[2] = N.z;
-                res.p[0] = I.x; res.p[1] = I.y; res.p[2] = I.z;
-                if (h.tri != 0xFFFFFFFFu && !(h.prim & BPT_HIT_PLANE) && sc.primitives[h.prim].type == BPT_PRIM_MESH) {
-                    res.triangle = tri_original[h.tri];
-                }
-            }
-            out[i] = res;
-        }
-    }
+    ApiSrc<OCC> src = {sc, rays, out, tri_original, ignored};
+    persistent_trace<OCC, STATS>(sc, src, n, cursor, refill, ctr);
     if (STATS) flush_counters(stats, ctr, OCC);
-    flush_ray_counts(stats, cnt, OCC ? cnt : 0);
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        atomicAdd(&stats->v[0], (unsigned long long)n);
+        if (OCC) atomicAdd(&stats->v[1], (unsigned long long)n);
+    }
 }
 
 __global__ void k_reset_counters(uint32_t* counters, int which_mask) {

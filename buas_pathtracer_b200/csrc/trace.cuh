@@ -20,13 +20,33 @@ namespace bpt {
 
 struct RayT {
     V3 o, d, inv;
-    uint32_t neg;          // bit k = d_is_negative[k]  (intersection.h:13-24)
+    uint32_t neg;          // bit k = d_is_negative[k]  (intersection.h:13-24); bit 3 = "no NaN/inf can arise in a slab test"
 };
+
+// A ray is "tame" when every |d_k| is in [1e-20, 1e20] and every |o_k| < 1e15: then, for node boxes inside 1e15
+// (checked at upload, DScene::tame_bounds), inv*(o-p) and |inv|*r are finite and below 1e36, so no slab-test
+// intermediate is NaN or inf and the reference's ternary min/max (my_math.h:77-85) agree with FMNMX on every
+// comparison outcome (they can differ only in NaN handling and in the sign of a zero, which no comparison sees).
+#define BPT_RAY_TAME 8u
 
 BPT_D void make_ray(RayT& r, V3 o, V3 d) {
     r.o = o; r.d = d;
     r.inv = 1.0f / d;
     r.neg = (d.x < 0.0f ? 1u : 0u) | (d.y < 0.0f ? 2u : 0u) | (d.z < 0.0f ? 4u : 0u);
+    float dlo = fminf(fminf(fabsf(d.x), fabsf(d.y)), fabsf(d.z)), dhi = fmaxf(fmaxf(fabsf(d.x), fabsf(d.y)), fabsf(d.z));
+    float ohi = fmaxf(fmaxf(fabsf(o.x), fabsf(o.y)), fabsf(o.z));
+    if (dlo >= 1e-20f && dhi <= 1e20f && ohi < 1e15f) r.neg |= BPT_RAY_TAME;     // false for NaN inputs
+}
+
+// same test for tame rays (see make_ray): FMNMX instead of compare+select
+BPT_D bool slab_test_tame(const RayT& r, float px, float py, float pz, float rx, float ry, float rz, float& tn) {
+    float nx = r.inv.x*(r.o.x - px), ny = r.inv.y*(r.o.y - py), nz = r.inv.z*(r.o.z - pz);
+    float kx = fabsf(r.inv.x)*rx,    ky = fabsf(r.inv.y)*ry,    kz = fabsf(r.inv.z)*rz;
+    float t1x = -nx - kx, t1y = -ny - ky, t1z = -nz - kz;
+    float t2x = -nx + kx, t2y = -ny + ky, t2z = -nz + kz;
+    tn = fmaxf(fmaxf(t1x, t1y), t1z);
+    float tf = fminf(fminf(t2x, t2y), t2z);
+    return (tn < tf) && (tf > 0.0f);
 }
 
 // ray_intersect_bounding_volume (intersection.cpp:107-133) split into its t-independent part and tn
@@ -111,37 +131,49 @@ struct TraceCounters {   // per-thread, flushed by the caller
 
 #define BPT_STACK_DEPTH 64     // the reference's node_stack[64] (intersection.cpp:261, :445), far children only here
 
+// Per-lane traversal state.  begin() does what precedes the reference's node loop (planes + TLAS root pop); the
+// node / triangle / instance steps are driven by persistent_trace below, which is the ONLY traversal loop in the
+// library (render passes and the bpt_trace diagnostic both run it).
+struct TraversalStack {
+    uint32_t lf[BPT_STACK_DEPTH];
+    uint32_t ca[BPT_STACK_DEPTH];
+    float    tn[BPT_STACK_DEPTH];
+};
+
 template <bool OCCLUSION, bool STATS>
-BPT_D void trace_ray(const DScene& sc, V3 o, V3 d, float max_t, uint32_t ignored, HitRecord& out, TraceCounters& ctr) {
-    RayT wray;
-    make_ray(wray, o, d);
-    float t = max_t;
-    uint32_t hit_prim = BPT_HIT_MISS, hit_tri = 0xFFFFFFFFu;
-    float hit_v = 0.0f, hit_w = 0.0f;
-
-    // planes first, linearly (intersection.cpp:424-433); in occlusion mode a plane hit does not return early
-    for (uint32_t i = 0; i < sc.plane_count; ++i) {
-        const DPlane& pl = sc.planes[i];
-        if (plane_test(wray, v3(__ldg(&pl.n[0]), __ldg(&pl.n[1]), __ldg(&pl.n[2])), __ldg(&pl.d), t)) hit_prim = BPT_HIT_PLANE | i;
-    }
-
-    uint32_t stk_lf[BPT_STACK_DEPTH];
-    uint32_t stk_ca[BPT_STACK_DEPTH];
-    float    stk_tn[BPT_STACK_DEPTH];
-    int sp = 0;
-
+struct Traversal {
     enum { S_NODE, S_ITEMS, S_POP, S_DONE };
-    int state;
-    int level = 0;                       // 0 = TLAS, 1 = inside a mesh BLAS
-    RayT ray = wray;
-    const DNodeHalf* nodes = sc.tlas_nodes;
-    uint32_t cur_lf, cur_ca;
-    uint32_t leaf_i = 0, leaf_end = 0;   // TLAS leaf items still to test
-    int blas_sp = 0;
-    uint32_t cur_prim = 0, cur_tri_base = 0;
-    uint32_t c_pops = 0, c_inner = 0, c_leaves = 0;   // per intersect_mesh call (see STATS note below)
 
-    {   // TLAS root (popped and box-tested like any node, intersection.cpp:450-454)
+    RayT ray;                            // ray in the current space (world in the TLAS, object inside a BLAS)
+    V3 wo, wd;                           // world-space ray, restored when intersect_mesh "returns"
+    float t;
+    uint32_t hit_prim, hit_tri;
+    float hit_v, hit_w;
+    uint32_t cur_lf, cur_ca;
+    uint32_t leaf_i, leaf_end;           // TLAS leaf items still to test
+    uint32_t cur_prim, cur_tri_base, ignored;
+    const DNodeHalf* nodes;
+    int sp, blas_sp, state, level;       // level: 0 = TLAS, 1 = inside a mesh BLAS
+    uint32_t c_pops, c_inner, c_leaves;  // per intersect_mesh call; dropped on an occlusion early-out like g_stats
+    // the stack itself lives outside the struct (TraversalStack) so these scalars stay in registers
+
+    BPT_D bool done() const { return state == S_DONE; }
+
+    BPT_D void begin(const DScene& sc, V3 o, V3 d, float max_t, uint32_t ignored_prim, TraceCounters& ctr) {
+        wo = o; wd = d;
+        make_ray(ray, o, d);
+        t = max_t;
+        hit_prim = BPT_HIT_MISS; hit_tri = 0xFFFFFFFFu; hit_v = 0.0f; hit_w = 0.0f;
+        ignored = ignored_prim;
+        sp = 0; blas_sp = 0; level = 0; leaf_i = 0; leaf_end = 0; cur_prim = 0; cur_tri_base = 0;
+        c_pops = c_inner = c_leaves = 0;
+        nodes = sc.tlas_nodes;
+        // planes first, linearly (intersection.cpp:424-433); in occlusion mode a plane hit does not return early
+        for (uint32_t i = 0; i < sc.plane_count; ++i) {
+            const DPlane& pl = sc.planes[i];
+            if (plane_test(ray, v3(__ldg(&pl.n[0]), __ldg(&pl.n[1]), __ldg(&pl.n[2])), __ldg(&pl.d), t)) hit_prim = BPT_HIT_PLANE | i;
+        }
+        // TLAS root (popped and box-tested like any node, intersection.cpp:450-454)
         float4 q0 = __ldg(&nodes[0].q0), q1 = __ldg(&nodes[0].q1);
         float tn;
         bool hit = slab_test(ray, q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, tn) && (tn < t);
@@ -150,108 +182,182 @@ BPT_D void trace_ray(const DScene& sc, V3 o, V3 d, float max_t, uint32_t ignored
         state = hit ? S_NODE : S_DONE;
     }
 
-    while (state != S_DONE) {
-        if (state == S_NODE) {
-            uint32_t count = cur_ca & 0xFFFFu;
-            if (count == 0) {
-                // inner node: fetch the sibling pair, test both, enter near, push far
-                const DNodeHalf* pr = nodes + cur_lf;
+    BPT_D void result(HitRecord& out) const {
+        out.t = t; out.prim = hit_prim; out.tri = hit_tri; out.v = hit_v; out.w = hit_w;
+    }
+};
+
+// Persistent-warp traversal with lane refill and warp-level phase scheduling.
+//
+// Measured problem with a per-thread state machine (ncu, profiles/r1_trace_v1.txt): for incoherent rays only 3-8 of 32
+// lanes were active per issued instruction, because at any moment the lanes of a warp sit in different phases
+// (slab-testing a sibling pair / testing a triangle / transforming the ray into an instance / idle) and the warp
+// serialises over all of them every iteration, and because finished lanes idle until the slowest ray of the warp ends.
+// Here each lane still owns one ray (its Traversal stays in registers) but per iteration the WARP executes only
+// the phase that most of its lanes are waiting for -- ballot + popc pick it -- and "idle" is one of the phases: when
+// idle lanes are the largest group (and rays remain) they fetch new rays with one warp-aggregated atomicAdd and run
+// begin().  Every ray still performs exactly the reference's sequence of tests; only the interleaving between
+// independent rays changes.   Src supplies load(i, o, d, max_t, ignored) / store(i, hit).
+template <bool OCCLUSION, bool STATS, class Src>
+BPT_D void persistent_trace(const DScene& sc, Src& src, uint32_t n, uint32_t* cursor, uint32_t refill, TraceCounters& ctr) {
+    typedef Traversal<OCCLUSION, STATS> TV;
+    enum { P_IDLE = 0, P_INNER = 1, P_TRI = 2, P_ITEMS = 3 };
+    const uint32_t FULL = 0xFFFFFFFFu;
+    const uint32_t lane = threadIdx.x & 31u;
+    TV tv;
+    TraversalStack stk;
+    tv.state = TV::S_DONE;
+    int phase = P_IDLE;
+    uint32_t tri_k = 0;
+    bool exhausted = false;
+    uint32_t my_index = 0;
+    const bool tame = sc.tame_bounds != 0;
+
+    // after `tv.cur_*` changed: which phase does the lane wait for now
+    auto classify = [&]() {
+        uint32_t count = tv.cur_ca & 0xFFFFu;
+        if (count == 0) phase = P_INNER;
+        else if (tv.level == 1) { phase = P_TRI; tri_k = 0; if (STATS) { tv.c_leaves += 1; ctr.tris += count; } }
+        else { tv.leaf_i = tv.cur_lf; tv.leaf_end = tv.cur_lf + count; phase = P_ITEMS; }
+    };
+    auto finish = [&]() {
+        HitRecord h; tv.result(h); src.store(my_index, h);
+        phase = P_IDLE;
+    };
+    // the reference's "pop until a node survives its box re-test" (intersection.cpp:269-277, :450-454)
+    auto pop = [&]() {
+        for (;;) {
+            if (tv.level == 1 && tv.sp == tv.blas_sp) {
+                if (STATS) { ctr.blas_pops += tv.c_pops; ctr.blas_inner += tv.c_inner; ctr.blas_leaves += tv.c_leaves; }
+                tv.level = 0; tv.nodes = sc.tlas_nodes;
+                make_ray(tv.ray, tv.wo, tv.wd);
+                phase = P_ITEMS;            // intersect_mesh returned: continue the TLAS leaf's item loop
+                return;
+            }
+            if (tv.sp == 0) { finish(); return; }
+            --tv.sp;
+            if (stk.tn[tv.sp] < tv.t) { tv.cur_lf = stk.lf[tv.sp]; tv.cur_ca = stk.ca[tv.sp]; classify(); return; }
+        }
+    };
+
+    for (;;) {
+        uint32_t n_inner = __popc(__ballot_sync(FULL, phase == P_INNER));
+        uint32_t n_tri   = __popc(__ballot_sync(FULL, phase == P_TRI));
+        uint32_t n_items = __popc(__ballot_sync(FULL, phase == P_ITEMS));
+        uint32_t idle_mask = __ballot_sync(FULL, phase == P_IDLE);
+        uint32_t n_idle = exhausted ? 0u : __popc(idle_mask);
+        if ((n_inner | n_tri | n_items | n_idle) == 0u) break;
+
+        int run = P_INNER; uint32_t best = n_inner;
+        if (n_tri > best)   { best = n_tri;   run = P_TRI; }
+        if (n_items > best) { best = n_items; run = P_ITEMS; }
+        if (n_idle >= refill || n_idle > best) { run = P_IDLE; }
+
+        if (run == P_IDLE) {
+            uint32_t nid = __popc(idle_mask);
+            uint32_t base = 0;
+            if (lane == 0) base = atomicAdd(cursor, nid);
+            base = __shfl_sync(FULL, base, 0);
+            if (phase == P_IDLE) {
+                uint32_t idx = base + __popc(idle_mask & ((1u << lane) - 1u));
+                if (idx < n) {
+                    V3 o, d; float max_t; uint32_t ign;
+                    src.load(idx, o, d, max_t, ign);
+                    my_index = idx;
+                    tv.begin(sc, o, d, max_t, ign, ctr);
+                    if (tv.done()) finish(); else classify();
+                }
+            }
+            if (base + nid >= n) exhausted = true;
+        } else if (run == P_INNER) {
+          // stay in this phase while at least 3/4 of the lanes that started it still want it (1 vote instead of 4)
+          uint32_t keep = max(best - (best >> 2), 1u);
+          do {
+            if (phase == P_INNER) {
+                const DNodeHalf* pr = tv.nodes + tv.cur_lf;
                 float4 l0 = __ldg(&pr[0].q0), l1 = __ldg(&pr[0].q1);
                 float4 r0 = __ldg(&pr[1].q0), r1 = __ldg(&pr[1].q1);
                 float tnl, tnr;
-                bool hl = slab_test(ray, l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, tnl);
-                bool hr = slab_test(ray, r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, tnr);
-                if (STATS) { if (level) { c_pops += 2; c_inner += 1; } else ctr.tlas_pops += 2; }
-                bool right_first = (ray.neg >> (cur_ca >> 16)) & 1u;     // intersection.cpp:365-373, :509-517
+                bool hl, hr;
+                if (tame && (tv.ray.neg & BPT_RAY_TAME)) {
+                    hl = slab_test_tame(tv.ray, l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, tnl);
+                    hr = slab_test_tame(tv.ray, r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, tnr);
+                } else {
+                    hl = slab_test(tv.ray, l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, tnl);
+                    hr = slab_test(tv.ray, r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, tnr);
+                }
+                if (STATS) { if (tv.level) { tv.c_pops += 2; tv.c_inner += 1; } else ctr.tlas_pops += 2; }
+                bool right_first = (tv.ray.neg >> (tv.cur_ca >> 16)) & 1u;
                 bool  near_hit = right_first ? hr : hl,            far_hit = right_first ? hl : hr;
                 float near_tn  = right_first ? tnr : tnl,          far_tn  = right_first ? tnl : tnr;
                 uint32_t near_lf = __float_as_uint(right_first ? r1.z : l1.z), far_lf = __float_as_uint(right_first ? l1.z : r1.z);
                 uint32_t near_ca = __float_as_uint(right_first ? r1.w : l1.w), far_ca = __float_as_uint(right_first ? l1.w : r1.w);
-                if (far_hit && sp < BPT_STACK_DEPTH) {
-                    stk_lf[sp] = far_lf; stk_ca[sp] = far_ca; stk_tn[sp] = far_tn; ++sp;
+                if (far_hit && tv.sp < BPT_STACK_DEPTH) {
+                    stk.lf[tv.sp] = far_lf; stk.ca[tv.sp] = far_ca; stk.tn[tv.sp] = far_tn; ++tv.sp;
                 }
-                if (near_hit && near_tn < t) { cur_lf = near_lf; cur_ca = near_ca; }
-                else state = S_POP;
-            } else if (level == 1) {
-                // BLAS leaf: contiguous triangles in leaf order (intersection.cpp:285-307)
-                if (STATS) { c_leaves += 1; ctr.tris += count; }
-                const DTriangle* tri = sc.triangles + cur_tri_base + cur_lf;
-                for (uint32_t k = 0; k < count; ++k) {
-                    float4 a = __ldg(&tri[k].a_idx), e1 = __ldg(&tri[k].e1), e2 = __ldg(&tri[k].e2);
-                    if (triangle_test(ray, v3(a), v3(e1), v3(e2), t, hit_v, hit_w)) {
-                        hit_tri = cur_tri_base + cur_lf + k;
-                        hit_prim = cur_prim;     // == "hit_any" of the enclosing intersect_mesh call
-                        if (OCCLUSION) { out.t = t; out.prim = hit_prim; out.tri = hit_tri; out.v = hit_v; out.w = hit_w; return; }
+                if (near_hit && near_tn < tv.t) { tv.cur_lf = near_lf; tv.cur_ca = near_ca; classify(); }
+                else pop();
+            }
+          } while (__popc(__ballot_sync(FULL, phase == P_INNER)) >= keep);
+        } else if (run == P_TRI) {
+          uint32_t keep = max(best - (best >> 2), 1u);
+          do {
+            if (phase == P_TRI) {
+                uint32_t slot = tv.cur_tri_base + tv.cur_lf + tri_k;
+                const DTriangle* tri = sc.triangles + slot;
+                float4 a = __ldg(&tri->a_idx), e1 = __ldg(&tri->e1), e2 = __ldg(&tri->e2);
+                bool stop = false;
+                if (triangle_test(tv.ray, v3(a), v3(e1), v3(e2), tv.t, tv.hit_v, tv.hit_w)) {
+                    tv.hit_tri = slot;
+                    tv.hit_prim = tv.cur_prim;
+                    if (OCCLUSION) { finish(); stop = true; }
+                }
+                if (!stop && ++tri_k >= (tv.cur_ca & 0xFFFFu)) pop();
+            }
+          } while (__popc(__ballot_sync(FULL, phase == P_TRI)) >= keep);
+        } else {
+            if (phase == P_ITEMS) {
+                if (tv.leaf_i >= tv.leaf_end) {
+                    pop();
+                } else {
+                    uint32_t prim_index = __ldg(&sc.tlas_indices[tv.leaf_i++]);
+                    if (prim_index != tv.ignored) {
+                        const DPrimitive* prim = sc.primitives + prim_index;
+                        float4 m[3] = {__ldg(&prim->inv[0]), __ldg(&prim->inv[1]), __ldg(&prim->inv[2])};
+                        RayT oray;
+                        make_ray(oray, xform(m, tv.wo, 1.0f), xform(m, tv.wd, 0.0f));
+                        if (STATS) ctr.instances += 1;
+                        uint32_t type = __ldg(&prim->type);
+                        if (type == BPT_PRIM_SPHERE) {
+                            if (sphere_test(oray, __ldg(&prim->sphere_r), tv.t)) {
+                                tv.hit_prim = prim_index; tv.hit_tri = 0xFFFFFFFFu;
+                                if (OCCLUSION) finish();
+                            }
+                        } else if (type == BPT_PRIM_BOX) {
+                            if (box_test(oray, __ldg(&prim->box_r[0]), __ldg(&prim->box_r[1]), __ldg(&prim->box_r[2]), tv.t)) {
+                                tv.hit_prim = prim_index; tv.hit_tri = 0xFFFFFFFFu;
+                                if (OCCLUSION) finish();
+                            }
+                        } else if (type == BPT_PRIM_MESH) {
+                            const DMesh* mesh = sc.meshes + __ldg(&prim->mesh);
+                            const DNodeHalf* bn = sc.blas_nodes + __ldg(&mesh->node_base);
+                            if (STATS) { ctr.mesh_calls += 1; tv.c_pops = 1; tv.c_inner = 0; tv.c_leaves = 0; }
+                            float4 q0 = __ldg(&bn[0].q0), q1 = __ldg(&bn[0].q1);
+                            float tn;
+                            if (slab_test(oray, q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, tn) && (tn < tv.t)) {
+                                tv.level = 1; tv.ray = oray; tv.nodes = bn; tv.blas_sp = tv.sp;
+                                tv.cur_prim = prim_index; tv.cur_tri_base = __ldg(&mesh->tri_base);
+                                tv.cur_lf = __float_as_uint(q1.z); tv.cur_ca = __float_as_uint(q1.w);
+                                classify();
+                            } else if (STATS) {
+                                ctr.blas_pops += 1;
+                            }
+                        }
                     }
                 }
-                state = S_POP;
-            } else {
-                leaf_i = cur_lf; leaf_end = cur_lf + count;
-                state = S_ITEMS;
-            }
-        }
-
-        if (state == S_ITEMS) {
-            // one TLAS leaf item per iteration (intersection.cpp:461-500)
-            if (leaf_i >= leaf_end) {
-                state = S_POP;
-            } else {
-                uint32_t prim_index = __ldg(&sc.tlas_indices[leaf_i++]);
-                if (prim_index != ignored) {
-                    const DPrimitive* prim = sc.primitives + prim_index;
-                    float4 m0 = __ldg(&prim->inv[0]), m1 = __ldg(&prim->inv[1]), m2 = __ldg(&prim->inv[2]);
-                    float4 m[3] = {m0, m1, m2};
-                    RayT oray;
-                    make_ray(oray, xform(m, wray.o, 1.0f), xform(m, wray.d, 0.0f));     // transform_ray :403-409
-                    if (STATS) ctr.instances += 1;
-                    uint32_t type = __ldg(&prim->type);
-                    if (type == BPT_PRIM_SPHERE) {
-                        if (sphere_test(oray, __ldg(&prim->sphere_r), t)) {
-                            hit_prim = prim_index; hit_tri = 0xFFFFFFFFu;
-                            if (OCCLUSION) { out.t = t; out.prim = hit_prim; out.tri = hit_tri; out.v = 0; out.w = 0; return; }
-                        }
-                    } else if (type == BPT_PRIM_BOX) {
-                        if (box_test(oray, __ldg(&prim->box_r[0]), __ldg(&prim->box_r[1]), __ldg(&prim->box_r[2]), t)) {
-                            hit_prim = prim_index; hit_tri = 0xFFFFFFFFu;
-                            if (OCCLUSION) { out.t = t; out.prim = hit_prim; out.tri = hit_tri; out.v = 0; out.w = 0; return; }
-                        }
-                    } else if (type == BPT_PRIM_MESH) {
-                        const DMesh* mesh = sc.meshes + __ldg(&prim->mesh);
-                        const DNodeHalf* bn = sc.blas_nodes + __ldg(&mesh->node_base);
-                        if (STATS) { ctr.mesh_calls += 1; c_pops = 1; c_inner = 0; c_leaves = 0; }
-                        float4 q0 = __ldg(&bn[0].q0), q1 = __ldg(&bn[0].q1);
-                        float tn;
-                        if (slab_test(oray, q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, tn) && (tn < t)) {
-                            level = 1; ray = oray; nodes = bn; blas_sp = sp;
-                            cur_prim = prim_index; cur_tri_base = __ldg(&mesh->tri_base);
-                            cur_lf = __float_as_uint(q1.z); cur_ca = __float_as_uint(q1.w);
-                            state = S_NODE;
-                        } else if (STATS) {
-                            ctr.blas_pops += 1;      // root popped, box missed: the call ends with 1 traversal
-                        }
-                    }
-                }
-            }
-        }
-
-        if (state == S_POP) {
-            if (level == 1 && sp == blas_sp) {
-                // intersect_mesh returns: back to the TLAS leaf's item loop in world space
-                if (STATS) { ctr.blas_pops += c_pops; ctr.blas_inner += c_inner; ctr.blas_leaves += c_leaves; }
-                level = 0; ray = wray; nodes = sc.tlas_nodes;
-                state = S_ITEMS;
-            } else if (level == 0 && leaf_i < leaf_end) {
-                state = S_ITEMS;
-            } else if (sp == 0) {
-                state = S_DONE;
-            } else {
-                --sp;
-                if (stk_tn[sp] < t) { cur_lf = stk_lf[sp]; cur_ca = stk_ca[sp]; state = S_NODE; }
             }
         }
     }
-
-    out.t = t; out.prim = hit_prim; out.tri = hit_tri; out.v = hit_v; out.w = hit_w;
 }
 
 } // namespace bpt

@@ -99,6 +99,35 @@ def test_hit_ids_bit_exact_nested_boxes_spheres(renderer, nested):
     _hit_parity(renderer, nested, 320, 180, light_pos=(0, 26, 12), light_id=a.counts()["primitives"] - 1)
 
 
+def test_hit_ids_axis_aligned_and_degenerate_rays(renderer, ico6, inst):
+    """rays with exactly-zero direction components (inv_d = inf, 0*inf = NaN inside the slab test, SURVEY Appendix A
+    #2) take the exact ternary min/max path; denormal-small components too; results still match bit for bit"""
+    rng = np.random.RandomState(21)
+    n = 6000
+    for pair in (ico6, inst):
+        a, b = pair
+        renderer.upload_scene(a)
+        rays = np.zeros(n, capi.RAY_DTYPE)
+        o = (rng.rand(n, 3).astype(np.float32) - 0.5) * np.float32(12) + np.array([0, 9, 0], np.float32)
+        d = np.zeros((n, 3), np.float32)
+        kind = rng.randint(0, 4, n)
+        d[kind == 0] = (0, -1, 0)                                  # straight down
+        d[kind == 1] = np.array((0.6, -0.8, 0), np.float32)        # one zero component
+        d[kind == 2] = np.array((1e-39, -1, 1e-30), np.float32)    # denormal / tiny components
+        m3 = kind == 3
+        d[m3] = rng.randn(int(m3.sum()), 3); d[m3] /= np.linalg.norm(d[m3], axis=1, keepdims=True)
+        # snap some origins onto node-box planes so that (o - p) == 0 happens with inv = inf
+        nodes, _, _ = a.mesh_bvh(0)
+        pick = nodes[rng.randint(0, len(nodes), n)]
+        snap = rng.rand(n) < 0.5
+        o[snap, 0] = (pick["bv_p"][snap, 0] * np.float32(3.5)).astype(np.float32)
+        rays["o"] = o; rays["d"] = d; rays["max_t"] = np.finfo(np.float32).max
+        g = renderer.trace(rays, capi.TRACE_CLOSEST)
+        r = b.trace(rays, capi.TRACE_CLOSEST)
+        assert_hits_equal(g, r, capi.TRACE_CLOSEST, "axis-aligned")
+        assert np.count_nonzero(g["primitive"] != capi.HIT_MISS) > n // 10
+
+
 def test_traversal_counters_equal_g_stats(renderer, ico6, oracle):
     """TraversalStats (intersection.h:33-40): same pops / inner / leaf counts as the reference's binary traversal."""
     a, b = ico6

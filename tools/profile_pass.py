@@ -1,0 +1,43 @@
+"""Render a few passes of one BASELINE config -- the small, fixed command that ncu / compute-sanitizer wrap.
+    python tools/profile_pass.py [--config c2] [--passes 2] [--spp N] [--w W --h H]
+Prints per-stage CUDA-event times of the last pass (never quote a number printed under a profiler)."""
+import argparse
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import buas_pathtracer_b200 as B  # noqa: E402
+from buas_pathtracer_b200 import scenes  # noqa: E402
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--config", default="c2")
+ap.add_argument("--passes", type=int, default=2)
+ap.add_argument("--spp", type=int, default=0)
+ap.add_argument("--w", type=int, default=0)
+ap.add_argument("--h", type=int, default=0)
+ap.add_argument("--rows", type=str, default="")      # "y0:y1" sub-rect
+ap.add_argument("--stats", action="store_true")
+a = ap.parse_args()
+cfg = scenes.CONFIGS[a.config]
+w, h, spp = a.w or cfg["w"], a.h or cfg["h"], a.spp or cfg["spp"]
+s = B.Scene()
+cfg["build"](s, w, h)
+r = B.Renderer(0)
+r.upload_scene(s)
+r.film_resize(w, h)
+rect = None
+if a.rows:
+    y0, y1 = [int(v) for v in a.rows.split(":")]
+    rect = (0, y0, w, y1)
+r.set_detailed_timing(True)
+if a.stats:
+    r.stats_enable(True)
+for i in range(a.passes):
+    r.get_stats(reset=True)
+    r.render_pass(spp, rect=rect, frame_count=0)
+    r.sync()
+t = r.pass_timing()
+st = r.get_stats().as_dict()
+print({k: round(getattr(t, k), 3) if isinstance(getattr(t, k), float) else getattr(t, k) for k, _ in t._fields_})
+print(st)
+print("Mrays/s", st["rays"] / t.total_ms / 1e3, "Msamples/s", st["samples"] / t.total_ms / 1e3)
