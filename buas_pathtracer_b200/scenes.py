@@ -1,7 +1,7 @@
 """The five BASELINE.json configurations as scene recipes.
 
 Each recipe is a function `build(scene, w, h)` that only uses the builder calls both backends export
-(buas_pathtracer_b200.Scene for the product, oracle.ref_oracle.RefScene for the reference), so the very same
+(buas_pathtracer_b200.Scene for the product; the test oracle exposes the same calls over the reference), so the very same
 inputs reach both sides.  Geometry comes from the library's procedural generators (numpy arrays handed to both).
 """
 import math
