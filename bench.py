@@ -213,8 +213,7 @@ def main():
     bands = my_rows(h, rank, world)
 
     def render(frame_count):
-        for (y0, y1) in bands:
-            r.render_pass(spp, rect=(0, y0, w, y1), frame_count=frame_count)
+        r.render_pass_bands(spp, bands, frame_count=frame_count)   # this rank's row blocks as one workload
 
     def step(frame_count):
         render(frame_count)
@@ -239,7 +238,6 @@ def main():
         dist.barrier()
 
     # --- timed region: K steps, CUDA events on this rank, max over ranks ---
-    r.set_detailed_timing(True)
     r.get_stats(reset=True)
     clocks = ClockSampler(local_rank)
     clocks.start()
@@ -258,14 +256,13 @@ def main():
     ms_total = ev0.elapsed_time(ev1)
     st_timed = r.get_stats(reset=True)
 
-    # per-kernel breakdown: one more (untimed) pass with per-band timing read-out
-    for (y0, y1) in bands:
-        r.render_pass(spp, rect=(0, y0, w, y1), frame_count=0)
-        r.sync()
-        t = r.pass_timing()
-        trace_ms += t.trace_ms; shadow_ms += t.shadow_ms; shade_ms += t.shade_ms
-        splat_ms += t.splat_ms; raygen_ms += t.raygen_ms
-        launches += t.kernel_launches; trace_launches += t.trace_launches
+    # per-kernel breakdown: one more pass, batches serialised so that each kernel's own duration is measured
+    r.set_detailed_timing(True)                       # one batch at a time, CUDA events around every kernel
+    render(0)
+    r.sync()
+    t = r.pass_timing()
+    trace_ms, shadow_ms, shade_ms, splat_ms, raygen_ms = t.trace_ms, t.shadow_ms, t.shade_ms, t.splat_ms, t.raygen_ms
+    launches, trace_launches = t.kernel_launches, t.trace_launches
     r.set_detailed_timing(False)
 
     rays_step = st_timed.rays / max(1, args.steps)

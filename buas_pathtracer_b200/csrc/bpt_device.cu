@@ -45,19 +45,27 @@ struct bpt_ctx {
     bool film_owned = false;
     uint32_t film_w = 0, film_h = 0;
 
-    uint32_t max_slots = 0;               // capacity of the path-state arrays
-    DPathState st{};
-    DQueues q{};
-    std::vector<void*> state_allocs;
+    // Two independent batch pipelines (stream + path state + queues): consecutive batches alternate between them so
+    // the tail of one batch's persistent kernels overlaps the next batch's head.
+    struct Pipe {
+        cudaStream_t stream = nullptr;
+        cudaEvent_t done = nullptr;
+        uint32_t max_slots = 0;
+        DPathState st{};
+        DQueues q{};
+        std::vector<void*> allocs;
+        bpt_sample_record* d_records = nullptr;
+        uint64_t d_record_capacity = 0;
+    } pipes[2];
+    int n_pipes = 2;
+    int32_t* d_row_map = nullptr;
+    uint32_t row_map_capacity = 0;
 
     DStats* d_stats = nullptr;
     bool stats_enabled = false;
 
     bpt_sample_record* host_records = nullptr;
     uint64_t host_record_capacity = 0;
-    bpt_sample_record* d_records = nullptr;
-    uint64_t d_record_capacity = 0;
-
     bool detailed_timing = false;
     std::vector<TimedSpan> spans;
     size_t spans_used = 0;
@@ -89,40 +97,41 @@ void free_all(std::vector<void*>* v) {
     v->clear();
 }
 
-int ensure_state(bpt_ctx* ctx, uint32_t slots) {
-    if (slots <= ctx->max_slots) return BPT_OK;
-    free_all(&ctx->state_allocs);
-    ctx->max_slots = 0;
+int ensure_state(bpt_ctx* ctx, bpt_ctx::Pipe* pp, uint32_t slots) {
+    (void)ctx;
+    if (slots <= pp->max_slots) return BPT_OK;
+    free_all(&pp->allocs);
+    pp->max_slots = 0;
     auto alloc = [&](void** p, size_t bytes) -> int {
         CK(cudaMalloc(p, bytes));
-        ctx->state_allocs.push_back(*p);
+        pp->allocs.push_back(*p);
         return BPT_OK;
     };
     size_t n = slots;
     int rc = 0;
-    rc |= alloc((void**)&ctx->st.ray_o, n*16);
-    rc |= alloc((void**)&ctx->st.ray_d, n*16);
-    rc |= alloc((void**)&ctx->st.hit, n*16);
-    rc |= alloc((void**)&ctx->st.hit_w, n*4);
-    rc |= alloc((void**)&ctx->st.throughput, n*16);
-    rc |= alloc((void**)&ctx->st.radiance, n*16);
-    rc |= alloc((void**)&ctx->st.rng, n*16);
-    rc |= alloc((void**)&ctx->st.prev_n, n*16);
-    rc |= alloc((void**)&ctx->st.jitter, n*8);
-    rc |= alloc((void**)&ctx->st.mstack_at, n);
-    rc |= alloc((void**)&ctx->st.mstack, n*2*BPT_MATERIAL_STACK_DEPTH);
-    rc |= alloc((void**)&ctx->st.primary_d, n*16);
-    rc |= alloc((void**)&ctx->st.primary_o, n*16);
-    rc |= alloc((void**)&ctx->q.active[0], n*4);
-    rc |= alloc((void**)&ctx->q.active[1], n*4);
-    rc |= alloc((void**)&ctx->q.shadow, n*sizeof(DShadowItem));
-    rc |= alloc((void**)&ctx->q.counters, 256);
+    rc |= alloc((void**)&pp->st.ray_o, n*16);
+    rc |= alloc((void**)&pp->st.ray_d, n*16);
+    rc |= alloc((void**)&pp->st.hit, n*16);
+    rc |= alloc((void**)&pp->st.hit_w, n*4);
+    rc |= alloc((void**)&pp->st.throughput, n*16);
+    rc |= alloc((void**)&pp->st.radiance, n*16);
+    rc |= alloc((void**)&pp->st.rng, n*16);
+    rc |= alloc((void**)&pp->st.prev_n, n*16);
+    rc |= alloc((void**)&pp->st.jitter, n*8);
+    rc |= alloc((void**)&pp->st.mstack_at, n);
+    rc |= alloc((void**)&pp->st.mstack, n*2*BPT_MATERIAL_STACK_DEPTH);
+    rc |= alloc((void**)&pp->st.primary_d, n*16);
+    rc |= alloc((void**)&pp->st.primary_o, n*16);
+    rc |= alloc((void**)&pp->q.active[0], n*4);
+    rc |= alloc((void**)&pp->q.active[1], n*4);
+    rc |= alloc((void**)&pp->q.shadow, n*sizeof(DShadowItem));
+    rc |= alloc((void**)&pp->q.counters, 256);
     if (rc) return BPT_ERR_CUDA;
-    ctx->max_slots = slots;
+    pp->max_slots = slots;
     return BPT_OK;
 }
 
-void begin_span(bpt_ctx* ctx, int stage) {
+void begin_span(bpt_ctx* ctx, int stage, cudaStream_t stream) {
     if (!ctx->detailed_timing) return;
     if (ctx->spans_used == ctx->spans.size()) {
         TimedSpan s; s.stage = stage;
@@ -130,12 +139,12 @@ void begin_span(bpt_ctx* ctx, int stage) {
         ctx->spans.push_back(s);
     }
     ctx->spans[ctx->spans_used].stage = stage;
-    cudaEventRecord(ctx->spans[ctx->spans_used].a, ctx->stream);
+    cudaEventRecord(ctx->spans[ctx->spans_used].a, stream);
 }
 
-void end_span(bpt_ctx* ctx) {
+void end_span(bpt_ctx* ctx, cudaStream_t stream) {
     if (!ctx->detailed_timing) return;
-    cudaEventRecord(ctx->spans[ctx->spans_used].b, ctx->stream);
+    cudaEventRecord(ctx->spans[ctx->spans_used].b, stream);
     ctx->spans_used++;
 }
 
@@ -182,6 +191,10 @@ int bpt_create(int device, bpt_ctx** out_ctx) {
     CK(cudaGetDeviceProperties(&prop, device));
     ctx->sm_count = prop.multiProcessorCount;
     CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    for (auto& pp : ctx->pipes) {
+        CK(cudaStreamCreateWithFlags(&pp.stream, cudaStreamNonBlocking));
+        CK(cudaEventCreateWithFlags(&pp.done, cudaEventDisableTiming));
+    }
     CK(cudaMalloc((void**)&ctx->d_stats, sizeof(DStats)));
     CK(cudaMemset(ctx->d_stats, 0, sizeof(DStats)));
     CK(cudaMalloc((void**)&ctx->d_filter, 512*sizeof(float)));
@@ -195,6 +208,7 @@ int bpt_create(int device, bpt_ctx** out_ctx) {
         if (m > 0) ctx->trace_ctas_per_sm = m;
     }
     if (const char* e = getenv("BPT_REFILL")) { int v = atoi(e); if (v >= 1 && v <= 33) ctx->refill = (uint32_t)v; }
+    if (const char* e = getenv("BPT_PIPES")) { int v = atoi(e); if (v >= 1 && v <= 2) ctx->n_pipes = v; }
     if (const char* e = getenv("BPT_TRACE_CTAS")) { int v = atoi(e); if (v >= 1 && v <= 32) ctx->trace_ctas_per_sm = v; }
     const char* dt = getenv("BPT_DETAILED_TIMING");
     ctx->detailed_timing = dt && atoi(dt) != 0;
@@ -207,11 +221,17 @@ void bpt_destroy(bpt_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     free_all(&ctx->scene_allocs);
-    free_all(&ctx->state_allocs);
+    for (auto& pp : ctx->pipes) {
+        cudaStreamSynchronize(pp.stream);
+        free_all(&pp.allocs);
+        cudaFree(pp.d_records);
+        cudaEventDestroy(pp.done);
+        cudaStreamDestroy(pp.stream);
+    }
+    cudaFree(ctx->d_row_map);
     if (ctx->film_owned && ctx->film) cudaFree(ctx->film);
     cudaFree(ctx->d_stats); cudaFree(ctx->d_filter);
     cudaFree(ctx->d_perm); cudaFree(ctx->d_sobol); cudaFree(ctx->d_scramble); cudaFree(ctx->d_rank);
-    cudaFree(ctx->d_records);
     for (auto& s : ctx->spans) { cudaEventDestroy(s.a); cudaEventDestroy(s.b); }
     cudaEventDestroy(ctx->pass_begin); cudaEventDestroy(ctx->pass_end);
     cudaStreamDestroy(ctx->stream);
@@ -498,129 +518,193 @@ int bpt_trace(bpt_ctx* ctx, uint32_t n, const bpt_ray* rays, int mode, uint32_t 
     return BPT_OK;
 }
 
-int bpt_render_pass(bpt_ctx* ctx, int32_t x0, int32_t y0, int32_t x1, int32_t y1,
-                    uint32_t frame_count, uint32_t spp, uint32_t seed_mode, uint32_t seed_salt) {
-    if (!ctx) { set_error("bpt_render_pass: null ctx"); return BPT_ERR_ARG; }
-    if (!ctx->scene_ready) { set_error("bpt_render_pass: no scene uploaded"); return BPT_ERR_STATE; }
-    if (!ctx->tables_ready) { set_error("bpt_render_pass: sampler tables not set (bpt_set_sampler_tables)"); return BPT_ERR_STATE; }
-    if (!ctx->film) { set_error("bpt_render_pass: no film (bpt_film_resize)"); return BPT_ERR_STATE; }
-    if (seed_mode != BPT_SEED_PER_PIXEL) { set_error("bpt_render_pass: unknown seed mode"); return BPT_ERR_ARG; }
-    if (x0 < 0 || y0 < 0 || x1 > (int32_t)ctx->film_w || y1 > (int32_t)ctx->film_h || x0 >= x1 || y0 >= y1 || spp == 0) {
-        set_error("bpt_render_pass: bad rect/spp"); return BPT_ERR_ARG;
-    }
+static int render_rows(bpt_ctx* ctx, int32_t x0, int32_t x1, const std::vector<int32_t>& rows,
+                       uint32_t frame_count, uint32_t spp, uint32_t seed_mode, uint32_t seed_salt, const char* who) {
+    if (!ctx->scene_ready) { set_error("%s: no scene uploaded", who); return BPT_ERR_STATE; }
+    if (!ctx->tables_ready) { set_error("%s: sampler tables not set (bpt_set_sampler_tables)", who); return BPT_ERR_STATE; }
+    if (!ctx->film) { set_error("%s: no film (bpt_film_resize)", who); return BPT_ERR_STATE; }
+    if (seed_mode != BPT_SEED_PER_PIXEL) { set_error("%s: unknown seed mode", who); return BPT_ERR_ARG; }
+    if (x0 < 0 || x1 > (int32_t)ctx->film_w || x0 >= x1 || rows.empty() || spp == 0) { set_error("%s: bad rect/spp", who); return BPT_ERR_ARG; }
+    for (int32_t y : rows) if (y < 0 || y >= (int32_t)ctx->film_h) { set_error("%s: bad rect/spp (row %d)", who, y); return BPT_ERR_ARG; }
     if (ctx->sc.settings.integrator != BPT_INTEGRATOR_ADVANCED) {
-        set_error("bpt_render_pass: only the \"Advanced Pathtracer\" integrator runs on the device (SURVEY 8a5)");
+        set_error("%s: only the \"Advanced Pathtracer\" integrator runs on the device (SURVEY 8a5)", who);
         return BPT_ERR_UNSUPPORTED;
     }
-    if (ctx->sc.filter_lut_size != 0 && ctx->sc.filter_radius == 0) { set_error("bpt_render_pass: filter LUT with radius 0"); return BPT_ERR_ARG; }
+    if (ctx->sc.filter_lut_size != 0 && ctx->sc.filter_radius == 0) { set_error("%s: filter LUT with radius 0", who); return BPT_ERR_ARG; }
     CK(cudaSetDevice(ctx->device));
 
     DScene& sc = ctx->sc;
     sc.film_w = ctx->film_w; sc.film_h = ctx->film_h;
-    uint32_t rect_w = (uint32_t)(x1 - x0), rect_h = (uint32_t)(y1 - y0);
-
-    // batch shape
-    uint64_t cap = 16ull << 20;
-    if (const char* e = getenv("BPT_MAX_SLOTS")) { uint64_t v = strtoull(e, nullptr, 10); if (v >= 1024) cap = v; }
-    uint32_t S = (uint32_t)std::min<uint64_t>(spp, std::max<uint64_t>(1, cap / rect_w));
-    uint32_t rows_per_batch = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(rect_h, cap / ((uint64_t)rect_w*S)));
-    uint64_t slots64 = (uint64_t)rect_w*rows_per_batch*S;
-    if (slots64 > 0x7FFFFFFFull) { set_error("bpt_render_pass: batch too large"); return BPT_ERR_ARG; }
-    int rc = ensure_state(ctx, (uint32_t)slots64);
-    if (rc) return rc;
+    uint32_t rect_w = (uint32_t)(x1 - x0), rect_h = (uint32_t)rows.size();
 
     bool want_records = ctx->host_records != nullptr;
-    uint64_t total_samples = (uint64_t)rect_w*rect_h*spp;
-    if (want_records) {
-        if (ctx->host_record_capacity < total_samples) { set_error("bpt_render_pass: record buffer too small"); return BPT_ERR_ARG; }
-        if (S != spp) { set_error("bpt_render_pass: records need all samples of a pixel in one batch (lower spp or raise BPT_MAX_SLOTS)"); return BPT_ERR_UNSUPPORTED; }
-        if (ctx->d_record_capacity < slots64) {
-            cudaFree(ctx->d_records); ctx->d_records = nullptr; ctx->d_record_capacity = 0;
-            CK(cudaMalloc((void**)&ctx->d_records, slots64*sizeof(bpt_sample_record)));
-            ctx->d_record_capacity = slots64;
+    // per-stage timing and record read-back want one batch at a time; otherwise two pipelines overlap
+    int n_pipes = (ctx->detailed_timing || want_records) ? 1 : ctx->n_pipes;
+
+    // batch shape
+    uint64_t cap = 64ull << 20;        // 64 Mi path slots per pipeline (~23 GB of path state each): few, large batches
+    if (const char* e = getenv("BPT_MAX_SLOTS")) { uint64_t v = strtoull(e, nullptr, 10); if (v >= 1024) cap = v; }
+    uint32_t S, rows_per_batch;
+    uint64_t n_batches;
+retry_shape:
+    S = (uint32_t)std::min<uint64_t>(spp, std::max<uint64_t>(1, cap / rect_w));
+    rows_per_batch = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(rect_h, cap / ((uint64_t)rect_w*S)));
+    n_batches = (uint64_t)((spp + S - 1)/S) * ((rect_h + rows_per_batch - 1)/rows_per_batch);
+    if (n_batches < (uint64_t)n_pipes) n_pipes = 1;
+    if (n_pipes == 2 && ((rect_h + rows_per_batch - 1)/rows_per_batch) & 1) {
+        // even out the last pair of batches
+        uint32_t nb = (rect_h + rows_per_batch - 1)/rows_per_batch + 1;
+        rows_per_batch = (rect_h + nb - 1)/nb;
+    }
+    uint64_t slots64 = (uint64_t)rect_w*rows_per_batch*S;
+    if (slots64 > 0x7FFFFFFFull) { set_error("%s: batch too large", who); return BPT_ERR_ARG; }
+    for (int p = 0; p < n_pipes; ++p) {
+        int rc = ensure_state(ctx, &ctx->pipes[p], (uint32_t)slots64);
+        if (rc) {
+            // out of device memory for this batch size: halve the batch and retry (the film/scene stay resident)
+            cudaGetLastError();
+            for (auto& pp : ctx->pipes) { free_all(&pp.allocs); pp.max_slots = 0; }
+            if (cap <= (1ull << 20)) return rc;
+            cap >>= 1;
+            goto retry_shape;
         }
     }
 
+    uint64_t total_samples = (uint64_t)rect_w*rect_h*spp;
+    if (want_records) {
+        bpt_ctx::Pipe& pp = ctx->pipes[0];
+        if (ctx->host_record_capacity < total_samples) { set_error("%s: record buffer too small", who); return BPT_ERR_ARG; }
+        if (S != spp) { set_error("%s: records need all samples of a pixel in one batch (lower spp or raise BPT_MAX_SLOTS)", who); return BPT_ERR_UNSUPPORTED; }
+        if (pp.d_record_capacity < slots64) {
+            cudaFree(pp.d_records); pp.d_records = nullptr; pp.d_record_capacity = 0;
+            CK(cudaMalloc((void**)&pp.d_records, slots64*sizeof(bpt_sample_record)));
+            pp.d_record_capacity = slots64;
+        }
+    }
+
+    if (ctx->row_map_capacity < rect_h) {
+        CK(cudaStreamSynchronize(ctx->stream));
+        for (auto& pp : ctx->pipes) CK(cudaStreamSynchronize(pp.stream));
+        cudaFree(ctx->d_row_map); ctx->d_row_map = nullptr; ctx->row_map_capacity = 0;
+        CK(cudaMalloc((void**)&ctx->d_row_map, (size_t)std::max<uint32_t>(rect_h, 4096)*sizeof(int32_t)));
+        ctx->row_map_capacity = std::max<uint32_t>(rect_h, 4096);
+    }
+    // the previous pass may still be reading the old row map on the pipe streams: order the copy after them
+    for (int p = 0; p < 2; ++p) { CK(cudaEventRecord(ctx->pipes[p].done, ctx->pipes[p].stream)); CK(cudaStreamWaitEvent(ctx->stream, ctx->pipes[p].done, 0)); }
+    CK(cudaMemcpyAsync(ctx->d_row_map, rows.data(), (size_t)rect_h*sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+
     ctx->spans_used = 0;
     ctx->launches = 0; ctx->trace_launches = 0;
-    cudaStream_t s = ctx->stream;
-    CK(cudaEventRecord(ctx->pass_begin, s));
+    CK(cudaEventRecord(ctx->pass_begin, ctx->stream));
+    for (int p = 0; p < n_pipes; ++p) CK(cudaStreamWaitEvent(ctx->pipes[p].stream, ctx->pass_begin, 0));
     const bool stats = ctx->stats_enabled;
     uint32_t max_bounce = sc.settings.max_bounce_count;
+    uint32_t batch_index = 0;
 
     for (uint32_t sa = 0; sa < spp; sa += S) {
         uint32_t Sb = std::min(S, spp - sa);
-        for (uint32_t row = 0; row < rect_h; row += rows_per_batch) {
+        for (uint32_t row = 0; row < rect_h; row += rows_per_batch, ++batch_index) {
+            bpt_ctx::Pipe& pp = ctx->pipes[batch_index % n_pipes];
+            cudaStream_t s = pp.stream;
             BatchDesc b;
-            b.x0 = x0; b.ya = y0 + (int32_t)row;
+            b.x0 = x0; b.row0 = row; b.row_map = ctx->d_row_map;
             b.rect_w = rect_w; b.rows = std::min(rows_per_batch, rect_h - row);
             b.sa = sa; b.S = Sb;
             b.frame_count = frame_count; b.salt = seed_salt;
             b.slots = rect_w*b.rows*Sb;
             b.want_records = want_records ? 1u : 0u;
 
-            begin_span(ctx, ST_RAYGEN);
-            k_raygen<<<grid_for(ctx, b.slots, 256, 8), 256, 0, s>>>(sc, ctx->st, b);
-            end_span(ctx);
+            begin_span(ctx, ST_RAYGEN, s);
+            k_raygen<<<grid_for(ctx, b.slots, 256, 8), 256, 0, s>>>(sc, pp.st, b);
+            end_span(ctx, s);
             ctx->launches++;
 
-            uint32_t* counters = ctx->q.counters;
+            uint32_t* counters = pp.q.counters;
             for (uint32_t bounce = 0; bounce < max_bounce; ++bounce) {
                 int in = bounce & 1, out = in ^ 1;
                 // counters: [in] = active count for this bounce (bounce 0 uses the identity queue), [out] and [2] (shadow) reset
-                const uint32_t* in_queue = bounce == 0 ? nullptr : ctx->q.active[in];
+                const uint32_t* in_queue = bounce == 0 ? nullptr : pp.q.active[in];
                 const uint32_t* in_count = bounce == 0 ? nullptr : counters + in;
                 k_reset_counters<<<1, 32, 0, s>>>(counters, (1 << out) | (1 << 2) | (1 << 3) | (1 << 4));
                 ctx->launches++;
                 uint32_t work = b.slots;    // upper bound; kernels read the true count on the device
 
-                begin_span(ctx, ST_TRACE);
+                begin_span(ctx, ST_TRACE, s);
                 uint32_t tg = grid_for(ctx, work, 128, ctx->trace_ctas_per_sm);
-                if (stats) k_trace_closest<true ><<<tg, 128, 0, s>>>(sc, ctx->st, in_queue, in_count, b.slots, counters + 3, ctx->refill, ctx->d_stats);
-                else       k_trace_closest<false><<<tg, 128, 0, s>>>(sc, ctx->st, in_queue, in_count, b.slots, counters + 3, ctx->refill, ctx->d_stats);
-                end_span(ctx);
+                if (stats) k_trace_closest<true ><<<tg, 128, 0, s>>>(sc, pp.st, in_queue, in_count, b.slots, counters + 3, ctx->refill, ctx->d_stats);
+                else       k_trace_closest<false><<<tg, 128, 0, s>>>(sc, pp.st, in_queue, in_count, b.slots, counters + 3, ctx->refill, ctx->d_stats);
+                end_span(ctx, s);
                 ctx->launches++; ctx->trace_launches++;
 
-                begin_span(ctx, ST_SHADE);
-                k_shade<<<grid_for(ctx, work, 128, 16), 128, 0, s>>>(sc, ctx->st, b, bounce, in_queue, in_count, b.slots,
-                                                                    ctx->q.active[out], counters + out, ctx->q.shadow, counters + 2, ctx->d_stats);
-                end_span(ctx);
+                begin_span(ctx, ST_SHADE, s);
+                k_shade<<<grid_for(ctx, work, 128, 16), 128, 0, s>>>(sc, pp.st, b, bounce, in_queue, in_count, b.slots,
+                                                                    pp.q.active[out], counters + out, pp.q.shadow, counters + 2, ctx->d_stats);
+                end_span(ctx, s);
                 ctx->launches++;
 
-                begin_span(ctx, ST_SHADOW);
-                if (stats) k_trace_shadow<true ><<<tg, 128, 0, s>>>(sc, ctx->st, ctx->q.shadow, counters + 2, counters + 4, ctx->refill, ctx->d_stats);
-                else       k_trace_shadow<false><<<tg, 128, 0, s>>>(sc, ctx->st, ctx->q.shadow, counters + 2, counters + 4, ctx->refill, ctx->d_stats);
-                end_span(ctx);
+                begin_span(ctx, ST_SHADOW, s);
+                if (stats) k_trace_shadow<true ><<<tg, 128, 0, s>>>(sc, pp.st, pp.q.shadow, counters + 2, counters + 4, ctx->refill, ctx->d_stats);
+                else       k_trace_shadow<false><<<tg, 128, 0, s>>>(sc, pp.st, pp.q.shadow, counters + 2, counters + 4, ctx->refill, ctx->d_stats);
+                end_span(ctx, s);
                 ctx->launches++; ctx->trace_launches++;
             }
 
-            begin_span(ctx, ST_SPLAT);
+            begin_span(ctx, ST_SPLAT, s);
             uint32_t pixels = rect_w*b.rows;
             if (sc.filter_lut_size != 0 && sc.filter_radius == 2) {
-                k_splat<2><<<grid_for(ctx, pixels, 128, 16), 128, 0, s>>>(sc, ctx->st, b, ctx->film);
+                k_splat<2><<<grid_for(ctx, pixels, 128, 16), 128, 0, s>>>(sc, pp.st, b, ctx->film);
             } else {
-                k_splat_generic<<<grid_for(ctx, b.slots, 128, 16), 128, 0, s>>>(sc, ctx->st, b, ctx->film);
+                k_splat_generic<<<grid_for(ctx, b.slots, 128, 16), 128, 0, s>>>(sc, pp.st, b, ctx->film);
             }
-            end_span(ctx);
+            end_span(ctx, s);
             ctx->launches++;
 
             if (want_records) {
-                k_write_records<<<grid_for(ctx, b.slots, 256, 8), 256, 0, s>>>(ctx->st, b, ctx->d_records);
+                k_write_records<<<grid_for(ctx, b.slots, 256, 8), 256, 0, s>>>(pp.st, b, pp.d_records);
                 ctx->launches++;
                 uint64_t first = (uint64_t)row*rect_w*spp;    // S == spp here: records are pixel-major / sample-minor
-                CK(cudaMemcpyAsync(ctx->host_records + first, ctx->d_records, (size_t)b.slots*sizeof(bpt_sample_record),
+                CK(cudaMemcpyAsync(ctx->host_records + first, pp.d_records, (size_t)b.slots*sizeof(bpt_sample_record),
                                    cudaMemcpyDeviceToHost, s));
                 CK(cudaStreamSynchronize(s));
                 ctx->d2h_bytes += (uint64_t)b.slots*sizeof(bpt_sample_record);
             }
         }
     }
-    CK(cudaEventRecord(ctx->pass_end, s));
+    for (int p = 0; p < n_pipes; ++p) {
+        CK(cudaEventRecord(ctx->pipes[p].done, ctx->pipes[p].stream));
+        CK(cudaStreamWaitEvent(ctx->stream, ctx->pipes[p].done, 0));
+    }
+    CK(cudaEventRecord(ctx->pass_end, ctx->stream));
     ctx->pass_recorded = true;
     ctx->total_launches += ctx->launches;
     ctx->samples += total_samples;
     CK(cudaGetLastError());
     return BPT_OK;
+}
+
+int bpt_render_pass(bpt_ctx* ctx, int32_t x0, int32_t y0, int32_t x1, int32_t y1,
+                    uint32_t frame_count, uint32_t spp, uint32_t seed_mode, uint32_t seed_salt) {
+    if (!ctx) { set_error("bpt_render_pass: null ctx"); return BPT_ERR_ARG; }
+    if (y0 < 0 || y0 >= y1 || y1 > (int32_t)ctx->film_h) {
+        if (!ctx->scene_ready) { set_error("bpt_render_pass: no scene uploaded"); return BPT_ERR_STATE; }
+        if (!ctx->film) { set_error("bpt_render_pass: no film (bpt_film_resize)"); return BPT_ERR_STATE; }
+        set_error("bpt_render_pass: bad rect/spp"); return BPT_ERR_ARG;
+    }
+    std::vector<int32_t> rows((size_t)(y1 - y0));
+    for (int32_t y = y0; y < y1; ++y) rows[(size_t)(y - y0)] = y;
+    return render_rows(ctx, x0, x1, rows, frame_count, spp, seed_mode, seed_salt, "bpt_render_pass");
+}
+
+int bpt_render_pass_bands(bpt_ctx* ctx, int32_t x0, int32_t x1, uint32_t n_bands, const int32_t* y0y1,
+                          uint32_t frame_count, uint32_t spp, uint32_t seed_mode, uint32_t seed_salt) {
+    if (!ctx || !y0y1 || n_bands == 0) { set_error("bpt_render_pass_bands: null argument"); return BPT_ERR_ARG; }
+    std::vector<int32_t> rows;
+    for (uint32_t i = 0; i < n_bands; ++i) {
+        int32_t a = y0y1[2*i], b = y0y1[2*i + 1];
+        if (a < 0 || a >= b || b > (int32_t)ctx->film_h) { set_error("bpt_render_pass_bands: bad band %u", i); return BPT_ERR_ARG; }
+        for (int32_t y = a; y < b; ++y) rows.push_back(y);
+    }
+    return render_rows(ctx, x0, x1, rows, frame_count, spp, seed_mode, seed_salt, "bpt_render_pass_bands");
 }
 
 int bpt_get_pass_timing(bpt_ctx* ctx, bpt_pass_timing* out) {

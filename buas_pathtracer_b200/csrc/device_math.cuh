@@ -78,6 +78,7 @@ BPT_D float exp_f(float x)  { return (float)exp((double)x); }
 BPT_D float atan2_f(float y, float x) { return (float)atan2((double)y, (double)x); }
 BPT_D float asin_f(float x) { return (float)asin((double)x); }
 BPT_D float pow_f(float x, float y) { return (float)pow((double)x, (double)y); }
+BPT_D void sincos_f(float x, float& s, float& c) { double ds, dc; sincos((double)x, &ds, &dc); s = (float)ds; c = (float)dc; }
 
 // ---- RNG (samplers.h:3-108): four xorshift32 lanes ----------------------------------------------------------------
 BPT_D uint32_t wang_hash(uint32_t key) {

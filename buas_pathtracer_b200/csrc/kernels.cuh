@@ -8,7 +8,9 @@ namespace bpt {
 
 // One batch = pixel rows [ya, yb) of the pass rect x samples [sa, sb).  slot = (row-major pixel in batch)*S + (s - sa)
 struct BatchDesc {
-    int32_t  x0, ya;          // first pixel column of the rect / first row of this batch
+    int32_t  x0;              // first pixel column of the rect
+    uint32_t row0;            // first entry of row_map this batch covers
+    const int32_t* row_map;   // device list of the pass's image rows (a rect, or a rank's interleaved row blocks)
     uint32_t rect_w, rows;    // rect width, rows in this batch
     uint32_t sa, S;           // first sample of this batch, samples per pixel in this batch
     uint32_t frame_count;     // AccumulationBuffer::frame_count of the pass
@@ -24,7 +26,7 @@ BPT_D SamplerCtx make_sampler(const DScene& sc, const BatchDesc& b, uint32_t slo
     c.strategy = sc.settings.sampling_strategy;
     c.index = b.frame_count + b.sa + s;
     c.x = (uint32_t)(b.x0 + (int32_t)(pix % b.rect_w));
-    c.y = (uint32_t)(b.ya + (int32_t)(pix / b.rect_w));
+    c.y = (uint32_t)__ldg(&b.row_map[b.row0 + pix / b.rect_w]);
     return c;
 }
 
@@ -96,7 +98,9 @@ BPT_D V3 map_to_hemisphere(V3 N, V2 u) {
     float azimuth = kTau*u.x;
     float y = u.y;
     float s = sqrtf(1.0f - y*y);
-    V3 hemi = v3(cos_f(azimuth)*s, y, sin_f(azimuth)*s);
+    float sn, cs;
+    sincos_f(azimuth, sn, cs);
+    V3 hemi = v3(cs*s, y, sn*s);
     return oriented_around_normal(hemi, N);
 }
 
@@ -104,7 +108,9 @@ BPT_D V3 map_to_cosine_weighted_hemisphere(V3 N, V2 u) {
     float azimuth = kTau*u.x;
     float y = u.y;
     float s = sqrtf(1.0f - y);
-    V3 hemi = v3(cos_f(azimuth)*s, sqrtf(y), sin_f(azimuth)*s);
+    float sn, cs;
+    sincos_f(azimuth, sn, cs);
+    V3 hemi = v3(cs*s, sqrtf(y), sn*s);
     return oriented_around_normal(hemi, N);
 }
 
@@ -286,6 +292,7 @@ BPT_D void flush_ray_counts(DStats* stats, uint32_t rays, uint32_t shadow) {
 struct ClosestSrc {        // rays come from the path state (through the active queue), hits go back to it
     DPathState st;
     const uint32_t* queue;
+    bool store_w;
     BPT_D void load(uint32_t i, V3& o, V3& d, float& max_t, uint32_t& ignored) const {
         uint32_t slot = queue ? queue[i] : i;
         float4 ro = st.ray_o[slot], rd = st.ray_d[slot];
@@ -294,7 +301,7 @@ struct ClosestSrc {        // rays come from the path state (through the active 
     BPT_D void store(uint32_t i, const HitRecord& h) const {
         uint32_t slot = queue ? queue[i] : i;
         st.hit[slot] = make_float4(h.t, __uint_as_float(h.prim), __uint_as_float(h.tri), h.v);
-        st.hit_w[slot] = h.w;
+        if (store_w) st.hit_w[slot] = h.w;      // barycentric w is only read for meshes with vertex normals
     }
 };
 
@@ -323,7 +330,7 @@ k_trace_closest(DScene sc, DPathState st, const uint32_t* __restrict__ in_queue,
                 uint32_t n_fixed, uint32_t* cursor, uint32_t refill, DStats* stats) {
     uint32_t n = n_ptr ? *n_ptr : n_fixed;
     TraceCounters ctr = {};
-    ClosestSrc src = {st, in_queue};
+    ClosestSrc src = {st, in_queue, sc.normals != nullptr};
     persistent_trace<false, STATS>(sc, src, n, cursor, refill, ctr);
     if (STATS) flush_counters(stats, ctr, false);
 }
@@ -376,16 +383,19 @@ k_shade(DScene sc, DPathState st, BatchDesc b, uint32_t bounce,
             float4 ro4 = st.ray_o[slot], rd4 = st.ray_d[slot], h4 = st.hit[slot];
             V3 ro = v3(ro4), rd = v3(rd4);
             HitRecord h;
-            h.t = h4.x; h.prim = __float_as_uint(h4.y); h.tri = __float_as_uint(h4.z); h.v = h4.w; h.w = st.hit_w[slot];
+            h.t = h4.x; h.prim = __float_as_uint(h4.y); h.tri = __float_as_uint(h4.z); h.v = h4.w; h.w = sc.normals ? st.hit_w[slot] : 0.0f;
             float4 tp4 = st.throughput[slot];
             V3 throughput = v3(tp4);
             float4 rad4 = st.radiance[slot];
             V3 total = v3(rad4);
-            float4 pd = st.primary_d[slot];
+            float4 pd = make_float4(0, 0, 0, 0);
+            if (b.want_records) pd = st.primary_d[slot];
             uint32_t ray_count = __float_as_uint(pd.w) + 1u;      // this bounce's intersect_scene call
+            bool total_changed = false;
 
             if (h.prim == BPT_HIT_MISS) {
                 total = total + throughput*sample_sky(sc, rd);                                     // :813
+                total_changed = true;
             } else {
                 SamplerCtx sm = make_sampler(sc, b, slot);
                 uint4 rng = st.rng[slot];
@@ -425,12 +435,14 @@ k_shade(DScene sc, DPathState st, BatchDesc b, uint32_t bounce,
                                          ((set.caustics || (bounce < 2)) && is_specular));
                     if (allow_direct) {
                         total = total + throughput*mt.emission;
+                        total_changed = true;
                     } else if (bounce > 0 && set.use_mis) {
                         float light_distance_sq = t*t;
                         float light_pdf = light_distance_sq / cos_i;
                         float brdf_pdf = (set.importance_sample_diffuse ? dot(prev_N, rd) / kPi : 1.0f / (2.0f*kPi));
                         float mis_pdf = light_pdf + brdf_pdf;
                         total = total + (1.0f / mis_pdf)*throughput*mt.emission;
+                        total_changed = true;
                     }
                 } else {
                     alive = true;
@@ -587,9 +599,8 @@ k_shade(DScene sc, DPathState st, BatchDesc b, uint32_t bounce,
                     }
                 }
             }
-            st.radiance[slot] = make_float4(total.x, total.y, total.z, 0.0f);
-            pd.w = __uint_as_float(ray_count);
-            st.primary_d[slot] = pd;
+            if (total_changed) st.radiance[slot] = make_float4(total.x, total.y, total.z, 0.0f);
+            if (b.want_records) { pd.w = __uint_as_float(ray_count); st.primary_d[slot] = pd; }
         }
 
         uint32_t qi = queue_append(out_count, alive);
@@ -610,7 +621,7 @@ k_splat(DScene sc, DPathState st, BatchDesc b, float4* __restrict__ film) {
     constexpr int SPAN = 2*R + 1;
     uint32_t pixels = b.rect_w*b.rows;
     for (uint32_t pix = blockIdx.x*blockDim.x + threadIdx.x; pix < pixels; pix += gridDim.x*blockDim.x) {
-        int x = b.x0 + (int)(pix % b.rect_w), y = b.ya + (int)(pix / b.rect_w);
+        int x = b.x0 + (int)(pix % b.rect_w), y = __ldg(&b.row_map[b.row0 + pix / b.rect_w]);
         float4 acc[SPAN*SPAN];
         #pragma unroll
         for (int k = 0; k < SPAN*SPAN; ++k) acc[k] = make_float4(0, 0, 0, 0);
@@ -659,7 +670,7 @@ k_splat_generic(DScene sc, DPathState st, BatchDesc b, float4* __restrict__ film
     int R = (int)sc.filter_radius;
     for (uint32_t slot = blockIdx.x*blockDim.x + threadIdx.x; slot < b.slots; slot += gridDim.x*blockDim.x) {
         uint32_t pix = slot / b.S;
-        int x = b.x0 + (int)(pix % b.rect_w), y = b.ya + (int)(pix / b.rect_w);
+        int x = b.x0 + (int)(pix % b.rect_w), y = __ldg(&b.row_map[b.row0 + pix / b.rect_w]);
         float4 rad = st.radiance[slot];
         float vig = st.throughput[slot].w;
         V3 c = v3(rad)*vig;

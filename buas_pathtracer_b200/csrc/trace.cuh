@@ -145,7 +145,8 @@ struct Traversal {
     enum { S_NODE, S_ITEMS, S_POP, S_DONE };
 
     RayT ray;                            // ray in the current space (world in the TLAS, object inside a BLAS)
-    V3 wo, wd;                           // world-space ray, restored when intersect_mesh "returns"
+    V3 wo, wd, winv;                     // world-space ray, restored when intersect_mesh "returns"
+    uint32_t wneg;
     float t;
     uint32_t hit_prim, hit_tri;
     float hit_v, hit_w;
@@ -162,6 +163,7 @@ struct Traversal {
     BPT_D void begin(const DScene& sc, V3 o, V3 d, float max_t, uint32_t ignored_prim, TraceCounters& ctr) {
         wo = o; wd = d;
         make_ray(ray, o, d);
+        winv = ray.inv; wneg = ray.neg;
         t = max_t;
         hit_prim = BPT_HIT_MISS; hit_tri = 0xFFFFFFFFu; hit_v = 0.0f; hit_w = 0.0f;
         ignored = ignored_prim;
@@ -230,7 +232,7 @@ BPT_D void persistent_trace(const DScene& sc, Src& src, uint32_t n, uint32_t* cu
             if (tv.level == 1 && tv.sp == tv.blas_sp) {
                 if (STATS) { ctr.blas_pops += tv.c_pops; ctr.blas_inner += tv.c_inner; ctr.blas_leaves += tv.c_leaves; }
                 tv.level = 0; tv.nodes = sc.tlas_nodes;
-                make_ray(tv.ray, tv.wo, tv.wd);
+                tv.ray.o = tv.wo; tv.ray.d = tv.wd; tv.ray.inv = tv.winv; tv.ray.neg = tv.wneg;   // == make_ray(wo, wd) again
                 phase = P_ITEMS;            // intersect_mesh returned: continue the TLAS leaf's item loop
                 return;
             }
@@ -325,9 +327,10 @@ BPT_D void persistent_trace(const DScene& sc, Src& src, uint32_t n, uint32_t* cu
                         const DPrimitive* prim = sc.primitives + prim_index;
                         float4 m[3] = {__ldg(&prim->inv[0]), __ldg(&prim->inv[1]), __ldg(&prim->inv[2])};
                         RayT oray;
-                        make_ray(oray, xform(m, tv.wo, 1.0f), xform(m, tv.wd, 0.0f));
+                        oray.o = xform(m, tv.wo, 1.0f); oray.d = xform(m, tv.wd, 0.0f);     // transform_ray :403-409
                         if (STATS) ctr.instances += 1;
                         uint32_t type = __ldg(&prim->type);
+                        if (type != BPT_PRIM_SPHERE) make_ray(oray, oray.o, oray.d);        // the sphere test never reads inv_d
                         if (type == BPT_PRIM_SPHERE) {
                             if (sphere_test(oray, __ldg(&prim->sphere_r), tv.t)) {
                                 tv.hit_prim = prim_index; tv.hit_tri = 0xFFFFFFFFu;

@@ -13,7 +13,7 @@ _LIB = None
 # every symbol include/bpt.h declares (checked by tests/test_abi.py against the header itself)
 DEVICE_SYMBOLS = [
     "create", "destroy", "set_sampler_tables", "upload_scene", "update_settings", "film_resize", "film_clear",
-    "film_use_external", "film_device_ptr", "download_film", "render_pass", "sync", "trace", "set_sample_records",
+    "film_use_external", "film_device_ptr", "download_film", "render_pass", "render_pass_bands", "sync", "trace", "set_sample_records",
     "stats_enable", "get_stats", "get_pass_timing", "set_detailed_timing", "get_transfer_bytes",
 ]
 MISC_SYMBOLS = ["last_error", "version", "make_displaced_icosphere", "make_procedural_skydome"]
@@ -75,6 +75,8 @@ def load_library():
     L.bpt_download_film.argtypes = [vp, vp]
     L.bpt_render_pass.restype = C.c_int
     L.bpt_render_pass.argtypes = [vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32]
+    L.bpt_render_pass_bands.restype = C.c_int
+    L.bpt_render_pass_bands.argtypes = [vp, C.c_int32, C.c_int32, C.c_uint32, vp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32]
     L.bpt_sync.restype = C.c_int
     L.bpt_sync.argtypes = [vp]
     L.bpt_trace.restype = C.c_int
@@ -178,6 +180,12 @@ class Renderer:
     def render_pass(self, spp, rect=None, frame_count=0, salt=0):
         x0, y0, x1, y1 = rect if rect else (0, 0, self.w, self.h)
         _check(self.lib.bpt_render_pass(self.handle, x0, y0, x1, y1, frame_count, spp, 0, salt), "bpt_render_pass")
+
+    def render_pass_bands(self, spp, bands, x0=0, x1=None, frame_count=0, salt=0):
+        """one pass over a list of row bands [(y0, y1), ...] as a single workload (a rank's share of the frame)"""
+        arr = np.ascontiguousarray(np.array(bands, dtype=np.int32).reshape(-1, 2))
+        _check(self.lib.bpt_render_pass_bands(self.handle, x0, self.w if x1 is None else x1, arr.shape[0], arr.ctypes.data,
+                                              frame_count, spp, 0, salt), "bpt_render_pass_bands")
 
     def sync(self):
         _check(self.lib.bpt_sync(self.handle), "bpt_sync")

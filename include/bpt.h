@@ -282,6 +282,10 @@ BPT_API int bpt_download_film(bpt_ctx* ctx, float* out_rgba /* w*h*4 floats, hos
  * stream; bpt_sync() or bpt_download_film() waits. */
 BPT_API int bpt_render_pass(bpt_ctx* ctx, int32_t x0, int32_t y0, int32_t x1, int32_t y1,
                             uint32_t frame_count, uint32_t spp, uint32_t seed_mode, uint32_t seed_salt);
+/* Same pass over a set of row bands [y0,y1) x [x0,x1) (n_bands pairs in y0y1) treated as ONE workload: the rows a
+ * rank owns under the multi-GPU row-block partition. */
+BPT_API int bpt_render_pass_bands(bpt_ctx* ctx, int32_t x0, int32_t x1, uint32_t n_bands, const int32_t* y0y1,
+                                  uint32_t frame_count, uint32_t spp, uint32_t seed_mode, uint32_t seed_salt);
 BPT_API int bpt_sync(bpt_ctx* ctx);
 
 /* Parity / diagnostics. */

@@ -17,6 +17,7 @@ ap.add_argument("--w", type=int, default=0)
 ap.add_argument("--h", type=int, default=0)
 ap.add_argument("--rows", type=str, default="")      # "y0:y1" sub-rect
 ap.add_argument("--stats", action="store_true")
+ap.add_argument("--no-detail", action="store_true")
 a = ap.parse_args()
 cfg = scenes.CONFIGS[a.config]
 w, h, spp = a.w or cfg["w"], a.h or cfg["h"], a.spp or cfg["spp"]
@@ -29,7 +30,7 @@ rect = None
 if a.rows:
     y0, y1 = [int(v) for v in a.rows.split(":")]
     rect = (0, y0, w, y1)
-r.set_detailed_timing(True)
+r.set_detailed_timing(not a.no_detail)
 if a.stats:
     r.stats_enable(True)
 for i in range(a.passes):
