@@ -103,7 +103,7 @@ def test_hit_ids_axis_aligned_and_degenerate_rays(renderer, ico6, inst):
     """rays with exactly-zero direction components (inv_d = inf, 0*inf = NaN inside the slab test, SURVEY Appendix A
     #2) take the exact ternary min/max path; denormal-small components too; results still match bit for bit"""
     rng = np.random.RandomState(21)
-    n = 6000
+    n = 3000
     for pair in (ico6, inst):
         a, b = pair
         renderer.upload_scene(a)
@@ -113,6 +113,8 @@ def test_hit_ids_axis_aligned_and_degenerate_rays(renderer, ico6, inst):
         kind = rng.randint(0, 4, n)
         d[kind == 0] = (0, -1, 0)                                  # straight down
         d[kind == 1] = np.array((0.6, -0.8, 0), np.float32)        # one zero component
+        hz = (kind == 1) & (rng.rand(n) < 0.5)
+        d[hz] = np.array((-0.24058728, 0.0, 0.9706275), np.float32)  # horizon ray: the reference pops ~6 M nodes for one of these
         d[kind == 2] = np.array((1e-39, -1, 1e-30), np.float32)    # denormal / tiny components
         m3 = kind == 3
         d[m3] = rng.randn(int(m3.sum()), 3); d[m3] /= np.linalg.norm(d[m3], axis=1, keepdims=True)
@@ -121,6 +123,7 @@ def test_hit_ids_axis_aligned_and_degenerate_rays(renderer, ico6, inst):
         pick = nodes[rng.randint(0, len(nodes), n)]
         snap = rng.rand(n) < 0.5
         o[snap, 0] = (pick["bv_p"][snap, 0] * np.float32(3.5)).astype(np.float32)
+        o[hz, 1] = rng.rand(int(hz.sum())).astype(np.float32) * np.float32(3.0)      # horizon rays through the meshes
         rays["o"] = o; rays["d"] = d; rays["max_t"] = np.finfo(np.float32).max
         g = renderer.trace(rays, capi.TRACE_CLOSEST)
         r = b.trace(rays, capi.TRACE_CLOSEST)
