@@ -94,6 +94,12 @@ class PassTiming(C.Structure):
                 ("kernel_launches", C.c_uint32), ("trace_launches", C.c_uint32)]
 
 
+class PostSettings(C.Structure):
+    """bpt_post_settings == PostProcessSettings (Raytracer/scene.h:84-90)"""
+    _fields_ = [("exposure", C.c_float), ("tonemapping", C.c_int32), ("srgb_transform", C.c_int32),
+                ("midpoint", C.c_float), ("contrast", C.c_float)]
+
+
 def _f3(v):
     return c_float3(*[float(x) for x in v])
 

@@ -725,6 +725,34 @@ int bpt_get_pass_timing(bpt_ctx* ctx, bpt_pass_timing* out) {
     return BPT_OK;
 }
 
+int bpt_resolve_bgra8(bpt_ctx* ctx, const bpt_post_settings* post, const uint8_t* dither_rgb8,
+                      uint32_t dither_w, uint32_t dither_h, uint32_t* out_pixels) {
+    if (!ctx || !post || !out_pixels) { set_error("bpt_resolve_bgra8: null argument"); return BPT_ERR_ARG; }
+    if (!ctx->film) { set_error("bpt_resolve_bgra8: no film"); return BPT_ERR_STATE; }
+    if (dither_rgb8 && (dither_w == 0 || dither_h == 0 || (dither_w & (dither_w - 1)) || (dither_h & (dither_h - 1)))) {
+        set_error("bpt_resolve_bgra8: dither tile must have power-of-two width and height"); return BPT_ERR_ARG;
+    }
+    CK(cudaSetDevice(ctx->device));
+    size_t n = (size_t)ctx->film_w*ctx->film_h;
+    uint32_t* d_out = nullptr; uint8_t* d_dither = nullptr;
+    CK(cudaMalloc((void**)&d_out, n*sizeof(uint32_t)));
+    if (dither_rgb8) {
+        size_t db = (size_t)dither_w*dither_h*3;
+        if (cudaMalloc((void**)&d_dither, db) != cudaSuccess) { cudaFree(d_out); set_error("bpt_resolve_bgra8: out of memory"); return BPT_ERR_CUDA; }
+        cudaMemcpyAsync(d_dither, dither_rgb8, db, cudaMemcpyHostToDevice, ctx->stream);
+        ctx->h2d_bytes += db;
+    }
+    k_resolve<<<grid_for(ctx, n, 256, 8), 256, 0, ctx->stream>>>(ctx->film, ctx->film_w, ctx->film_h, *post, d_dither, dither_w, dither_h, d_out);
+    ctx->total_launches += 1;
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out_pixels, d_out, n*sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d_out); cudaFree(d_dither);
+    if (e != cudaSuccess) { set_error("bpt_resolve_bgra8: %s", cudaGetErrorString(e)); return BPT_ERR_CUDA; }
+    ctx->d2h_bytes += n*sizeof(uint32_t);
+    return BPT_OK;
+}
+
 int bpt_set_detailed_timing(bpt_ctx* ctx, int enable) {
     if (!ctx) return BPT_ERR_ARG;
     ctx->detailed_timing = enable != 0;

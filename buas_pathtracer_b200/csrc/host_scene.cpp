@@ -360,6 +360,25 @@ int bpt_get_counts(const bpt_scene* s, uint32_t* materials, uint32_t* primitives
     return BPT_OK;
 }
 
+int bpt_write_bitmap(const char* file_name, const uint32_t* pixels, uint32_t w, uint32_t h) {
+    // write_bitmap (assets.cpp:671-724): BITMAPINFOHEADER, 32 bpp, negative height = top-down, 4096 px/m
+    if (!file_name || !pixels || w == 0 || h == 0) { set_error("bpt_write_bitmap: bad arguments"); return BPT_ERR_ARG; }
+    uint32_t pixel_size = 4u*w*h;
+    unsigned char hdr[54];
+    memset(hdr, 0, sizeof(hdr));
+    auto put16 = [&](int at, uint16_t v) { memcpy(hdr + at, &v, 2); };
+    auto put32 = [&](int at, uint32_t v) { memcpy(hdr + at, &v, 4); };
+    put16(0, 0x4D42); put32(2, 54 + pixel_size); put32(10, 54); put32(14, 40);
+    put32(18, w); put32(22, (uint32_t)(-(int32_t)h)); put16(26, 1); put16(28, 32);
+    put32(30, 0); put32(34, pixel_size); put32(38, 4096); put32(42, 4096);
+    FILE* f = fopen(file_name, "wb");
+    if (!f) { set_error("bpt_write_bitmap: cannot open %s", file_name); return BPT_ERR_ARG; }
+    bool ok = fwrite(hdr, 1, 54, f) == 54 && fwrite(pixels, 1, pixel_size, f) == pixel_size;
+    fclose(f);
+    if (!ok) { set_error("bpt_write_bitmap: short write to %s", file_name); return BPT_ERR_ARG; }
+    return BPT_OK;
+}
+
 // ---- procedural inputs for the BASELINE.json configs --------------------------------------------------------------
 
 uint32_t bpt_make_displaced_icosphere(uint32_t level, float amplitude, float* positions) {

@@ -754,6 +754,64 @@ k_trace_api(DScene sc, const bpt_ray* __restrict__ rays, uint32_t n, uint32_t ig
     }
 }
 
+// the display loop's per-pixel resolve (raytracer.cpp:2113-2172)
+BPT_D float sigmoidal_contrast(float x, float contrast, float midpoint) {       // raytracer.cpp:69-84
+    float curve;
+    if (x < midpoint) {
+        float scale = (1.0f / midpoint)*x;
+        curve = midpoint*(scale*scale);
+    } else {
+        float y = (1.0f / (1.0f - midpoint));
+        float scale = y - y*x;
+        curve = 1.0f - (1.0f - midpoint)*(scale*scale);
+    }
+    return lerp_f(x, curve, contrast);
+}
+
+BPT_D float remap_tpdf(float x) {                                                 // raytracer.cpp:125-132
+    float orig = 2.0f*x - 1.0f;
+    // the reference uses the SSE rsqrt approximation (12-bit); an exact 1/sqrt differs by < 1e-3 -> at most 1 LSB after dither
+    x = orig*rsqrtf(fabsf(orig));
+    x = max_t(-1.0f, x);
+    x = x - sign_of(x);
+    return x;
+}
+
+__global__ void k_resolve(const float4* __restrict__ film, uint32_t w, uint32_t h, bpt_post_settings post,
+                          const uint8_t* __restrict__ dither, uint32_t dw, uint32_t dh, uint32_t* __restrict__ out) {
+    uint32_t n = w*h;
+    for (uint32_t i = blockIdx.x*blockDim.x + threadIdx.x; i < n; i += gridDim.x*blockDim.x) {
+        float4 s = film[i];
+        V3 c = v3(0.0f);
+        if ((s.x != s.x) || (s.y != s.y) || (s.z != s.z) || (s.w != s.w)) {
+            c = v3(0.0f, 255.0f, 255.0f);
+        } else if (s.w > 0.001f) {
+            c = v3(s.x, s.y, s.z) / s.w;
+            c = v3(max_t(c.x, 0.0f), max_t(c.y, 0.0f), max_t(c.z, 0.0f));
+            if (post.exposure != 0.0f) c = c*pow_f(2.0f, post.exposure);
+            if (post.tonemapping) c = v3(1.0f - exp_f(-c.x), 1.0f - exp_f(-c.y), 1.0f - exp_f(-c.z));
+            if (post.srgb_transform) c = v3(pow_f(c.x, 1.0f / 2.23333f), pow_f(c.y, 1.0f / 2.23333f), pow_f(c.z, 1.0f / 2.23333f));
+            if (post.contrast != 0.0f) c = v3(sigmoidal_contrast(c.x, post.contrast, post.midpoint),
+                                              sigmoidal_contrast(c.y, post.contrast, post.midpoint),
+                                              sigmoidal_contrast(c.z, post.contrast, post.midpoint));
+            c = c*255.0f;
+            if (dither) {
+                uint32_t x = i % w, y = i / w;
+                const uint8_t* d = dither + ((size_t)(y & (dh - 1))*dw + (x & (dw - 1)))*3;
+                c = c + v3(0.5f + remap_tpdf((1.0f / 255.0f)*(float)d[0]),
+                           0.5f + remap_tpdf((1.0f / 255.0f)*(float)d[1]),
+                           0.5f + remap_tpdf((1.0f / 255.0f)*(float)d[2]));
+            }
+        } else if (s.w < -0.01f) {
+            c = v3(-255.0f*s.w, 0.0f, -255.0f*s.w);
+        }
+        uint32_t r = (uint32_t)(uint8_t)clamp_t(c.x, 0.0f, 255.0f);
+        uint32_t g = (uint32_t)(uint8_t)clamp_t(c.y, 0.0f, 255.0f);
+        uint32_t b = (uint32_t)(uint8_t)clamp_t(c.z, 0.0f, 255.0f);
+        out[i] = (255u << 24) | (r << 16) | (g << 8) | b;
+    }
+}
+
 __global__ void k_reset_counters(uint32_t* counters, int which_mask) {
     if (threadIdx.x < 8 && (which_mask >> threadIdx.x) & 1) counters[threadIdx.x] = 0;
 }

@@ -14,7 +14,7 @@ _LIB = None
 DEVICE_SYMBOLS = [
     "create", "destroy", "set_sampler_tables", "upload_scene", "update_settings", "film_resize", "film_clear",
     "film_use_external", "film_device_ptr", "download_film", "render_pass", "render_pass_bands", "sync", "trace", "set_sample_records",
-    "stats_enable", "get_stats", "get_pass_timing", "set_detailed_timing", "get_transfer_bytes",
+    "stats_enable", "get_stats", "get_pass_timing", "set_detailed_timing", "get_transfer_bytes", "resolve_bgra8",
 ]
 MISC_SYMBOLS = ["last_error", "version", "make_displaced_icosphere", "make_procedural_skydome"]
 
@@ -93,6 +93,10 @@ def load_library():
     L.bpt_set_detailed_timing.argtypes = [vp, C.c_int]
     L.bpt_get_transfer_bytes.restype = C.c_int
     L.bpt_get_transfer_bytes.argtypes = [vp, P(C.c_uint64), P(C.c_uint64), C.c_int]
+    L.bpt_resolve_bgra8.restype = C.c_int
+    L.bpt_resolve_bgra8.argtypes = [vp, P(capi.PostSettings), vp, C.c_uint32, C.c_uint32, vp]
+    L.bpt_write_bitmap.restype = C.c_int
+    L.bpt_write_bitmap.argtypes = [C.c_char_p, vp, C.c_uint32, C.c_uint32]
     _LIB = L
     return L
 
@@ -227,6 +231,18 @@ class Renderer:
         a, b = C.c_uint64(), C.c_uint64()
         _check(self.lib.bpt_get_transfer_bytes(self.handle, C.byref(a), C.byref(b), int(reset)), "bpt_get_transfer_bytes")
         return a.value, b.value
+
+    def resolve_bgra8(self, exposure=0.0, tonemapping=True, srgb_transform=True, midpoint=0.5, contrast=0.0, dither=None):
+        """film -> (h, w) uint32 0xAARRGGBB as the reference's display loop produces it (raytracer.cpp:2103-2172)"""
+        post = capi.PostSettings(exposure, int(tonemapping), int(srgb_transform), midpoint, contrast)
+        out = np.empty((self.h, self.w), np.uint32)
+        dp, dw, dh = None, 0, 0
+        if dither is not None:
+            dither = np.ascontiguousarray(dither, np.uint8)
+            dh, dw, _ = dither.shape
+            dp = dither.ctypes.data
+        _check(self.lib.bpt_resolve_bgra8(self.handle, C.byref(post), dp, dw, dh, out.ctypes.data), "bpt_resolve_bgra8")
+        return out
 
     def pass_timing(self):
         t = capi.PassTiming()

@@ -1,0 +1,141 @@
+// Headless driver: what is left of SDL_main (Raytracer/raytracer.cpp:1560-2390) once the Win32/SDL/microui shell is
+// removed -- build a scene, run progressive passes through the C ABI, "Take picture" (resolve + write_bitmap).
+//
+//   bpt_headless [--scene week3|icosphere] [--w W --h H] [--spp N] [--passes P] [--level L] [--device D] [--out file.bmp]
+//
+// It only speaks include/bpt.h (plain C), exactly like a binding inside the reference would.
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <chrono>
+#include <vector>
+
+#include "../include/bpt.h"
+
+static const float kDegToRad = 6.28318530717f / 360.0f;   // my_math.h:17
+
+static bpt_m4x4inv translate(float x, float y, float z, float s = 1.0f) {
+    bpt_m4x4inv m;
+    memset(&m, 0, sizeof(m));
+    for (int i = 0; i < 4; ++i) { m.forward.e[i][i] = i < 3 ? s : 1.0f; m.inverse.e[i][i] = i < 3 ? 1.0f/s : 1.0f; }
+    m.forward.e[0][3] = x; m.forward.e[1][3] = y; m.forward.e[2][3] = z;
+    m.inverse.e[0][3] = -x/s; m.inverse.e[1][3] = -y/s; m.inverse.e[2][3] = -z/s;   // (T*S)^-1 = S^-1 * T^-1
+    return m;
+}
+
+static void set_camera(bpt_scene* s, uint32_t w, uint32_t h, float px, float py, float pz, float vfov_deg) {
+    bpt_camera cam;
+    bpt_get_camera(s, &cam);
+    cam.vfov = kDegToRad*vfov_deg;
+    cam.aspect_ratio = (float)w / (float)h;
+    cam.lens_radius = 0.0f;
+    cam.focus_distance = 1.0f;
+    cam.p[0] = px; cam.p[1] = py; cam.p[2] = pz;
+    bpt_set_camera(s, &cam);
+}
+
+static void use_advanced_integrator(bpt_scene* s) {
+    bpt_settings st;
+    bpt_get_settings(s, &st);
+    st.integrator = bpt_find_integrator("Advanced Pathtracer");
+    st.lens_distortion = 0.0f;
+    bpt_set_settings(s, &st);
+    bpt_load_reconstruction_kernel(s, "Mitchell Netravali");
+}
+
+// week_3_scene (raytracer.cpp:840-861) with the advanced integrator = BASELINE config 1
+static void build_week3(bpt_scene* s, uint32_t w, uint32_t h) {
+    set_camera(s, w, h, 0, 4, -10, 60.0f);
+    const float d[3] = {0, 0, -1};
+    bpt_aim_camera(s, d);
+    use_advanced_integrator(s);
+    const float white[3] = {1, 1, 1}, black[3] = {0, 0, 0}, red[3] = {1, 0, 0}, grey[3] = {0.1f, 0.1f, 0.1f}, e[3] = {12500, 12500, 12500};
+    uint32_t ground = bpt_add_diffuse_material(s, white, 1.0f, 0.0f, 1, black);
+    uint32_t sphere = bpt_add_diffuse_material(s, red, 1.0f, 0.0f, 0, grey);
+    uint32_t light = bpt_add_emissive_material(s, e);
+    const float up[3] = {0, 1, 0};
+    bpt_add_plane(s, ground, up, 0.0f);
+    bpt_m4x4inv t1 = translate(0, 4, 0), t2 = translate(8, 16, -8);
+    bpt_add_sphere(s, sphere, 4.0f, &t1);
+    bpt_add_sphere(s, light, 0.1f, &t2);
+}
+
+// displaced icosphere under the TLAS = BASELINE config 2 (level 8 = 1,310,720 triangles)
+static void build_icosphere(bpt_scene* s, uint32_t w, uint32_t h, uint32_t level) {
+    set_camera(s, w, h, 0, 4.5f, -11, 50.0f);
+    const float at[3] = {0, 3.5f, 0};
+    bpt_aim_camera_at(s, at);
+    bpt_camera cam; bpt_get_camera(s, &cam); cam.focus_distance = 1.0f; bpt_set_camera(s, &cam);
+    use_advanced_integrator(s);
+    const float sky[3] = {0.45f, 0.6f, 0.9f};
+    bpt_set_sky(s, sky, sky);
+    const float g0[3] = {0.8f, 0.8f, 0.8f}, g1[3] = {0.25f, 0.25f, 0.25f}, clay[3] = {0.85f, 0.55f, 0.35f}, grey[3] = {0.1f, 0.1f, 0.1f}, e[3] = {4000, 3800, 3500};
+    uint32_t ground = bpt_add_diffuse_material(s, g0, 1.0f, 0.0f, 1, g1);
+    uint32_t mat = bpt_add_diffuse_material(s, clay, 1.0f, 0.0f, 0, grey);
+    uint32_t light = bpt_add_emissive_material(s, e);
+    const float up[3] = {0, 1, 0};
+    bpt_add_plane(s, ground, up, 0.0f);
+    uint32_t n = bpt_make_displaced_icosphere(level, 0.08f, nullptr);
+    std::vector<float> tris((size_t)n*9);
+    bpt_make_displaced_icosphere(level, 0.08f, tris.data());
+    uint32_t mesh = bpt_create_mesh(s, n, tris.data(), nullptr);
+    bpt_m4x4inv xf = translate(0, 3.6f, 0, 3.5f), lt = translate(9, 14, -9);
+    bpt_add_mesh(s, mat, mesh, &xf);
+    bpt_add_sphere(s, light, 0.5f, &lt);
+}
+
+#define CHECK(call) do { int rc_ = (call); if (rc_ != BPT_OK) { fprintf(stderr, "%s failed (%d): %s\n", #call, rc_, bpt_last_error()); return 1; } } while (0)
+
+int main(int argc, char** argv) {
+    const char* scene_name = "week3"; const char* out = "render.bmp"; const char* tables = nullptr;
+    uint32_t w = 640, h = 360, spp = 16, passes = 1, level = 6; int device = 0;
+    for (int i = 1; i < argc; ++i) {
+        auto next = [&]() -> const char* { return i + 1 < argc ? argv[++i] : ""; };
+        if (!strcmp(argv[i], "--scene")) scene_name = next();
+        else if (!strcmp(argv[i], "--w")) w = (uint32_t)atoi(next());
+        else if (!strcmp(argv[i], "--h")) h = (uint32_t)atoi(next());
+        else if (!strcmp(argv[i], "--spp")) spp = (uint32_t)atoi(next());
+        else if (!strcmp(argv[i], "--passes")) passes = (uint32_t)atoi(next());
+        else if (!strcmp(argv[i], "--level")) level = (uint32_t)atoi(next());
+        else if (!strcmp(argv[i], "--device")) device = atoi(next());
+        else if (!strcmp(argv[i], "--out")) out = next();
+        else if (!strcmp(argv[i], "--tables")) tables = next();
+        else { fprintf(stderr, "unknown argument %s\n", argv[i]); return 2; }
+    }
+    if (!tables) { fprintf(stderr, "--tables <sampler_tables.bin> is required (the sampler lookup tables, see INTEGRATION.md)\n"); return 2; }
+    std::vector<uint8_t> blob(16384 + 65536 + 131072 + 131072);
+    FILE* tf = fopen(tables, "rb");
+    if (!tf || fread(blob.data(), 1, blob.size(), tf) != blob.size()) { fprintf(stderr, "cannot read %s\n", tables); return 2; }
+    fclose(tf);
+
+    bpt_scene* scene = bpt_scene_create();
+    if (!strcmp(scene_name, "week3")) build_week3(scene, w, h);
+    else if (!strcmp(scene_name, "icosphere")) build_icosphere(scene, w, h, level);
+    else { fprintf(stderr, "unknown scene %s\n", scene_name); return 2; }
+    auto t0 = std::chrono::steady_clock::now();
+    CHECK(bpt_create_scene_bvh(scene));
+    printf("BVH Construction took: %fs\n", std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count());
+
+    bpt_ctx* ctx = nullptr;
+    CHECK(bpt_create(device, &ctx));                       // fails when there is no GPU: no CPU fallback
+    CHECK(bpt_set_sampler_tables(ctx, blob.data(), blob.data() + 16384, blob.data() + 81920, blob.data() + 212992));
+    CHECK(bpt_upload_scene(ctx, scene));
+    CHECK(bpt_film_resize(ctx, w, h));
+    t0 = std::chrono::steady_clock::now();
+    for (uint32_t p = 0; p < passes; ++p) CHECK(bpt_render_pass(ctx, 0, 0, (int32_t)w, (int32_t)h, p*spp, spp, BPT_SEED_PER_PIXEL, p));
+    CHECK(bpt_sync(ctx));
+    double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    bpt_stats st;
+    CHECK(bpt_get_stats(ctx, &st, 0));
+    printf("Took %ux%u %uspp image in %f seconds.  (%.1f Mrays/s, %.1f Msamples/s)\n", w, h, spp*passes, sec,
+           (double)st.rays/sec/1e6, (double)st.samples/sec/1e6);
+
+    bpt_post_settings post = {0.0f, 1, 1, 0.5f, 0.0f};      // init_scene defaults (raytracer.cpp:1450-1452)
+    std::vector<uint32_t> pixels((size_t)w*h);
+    CHECK(bpt_resolve_bgra8(ctx, &post, nullptr, 0, 0, pixels.data()));
+    CHECK(bpt_write_bitmap(out, pixels.data(), w, h));
+    printf("wrote %s\n", out);
+    bpt_destroy(ctx);
+    bpt_scene_destroy(scene);
+    return 0;
+}

@@ -288,6 +288,23 @@ BPT_API int bpt_render_pass_bands(bpt_ctx* ctx, int32_t x0, int32_t x1, uint32_t
                                   uint32_t frame_count, uint32_t spp, uint32_t seed_mode, uint32_t seed_salt);
 BPT_API int bpt_sync(bpt_ctx* ctx);
 
+/* ---- resolve + post-process + "Render to bitmap" (raytracer.cpp:2103-2185, assets.cpp:671-724) ---- */
+/* PostProcessSettings (Raytracer/scene.h:84-90) -- layout-compatible. */
+typedef struct bpt_post_settings {
+    float   exposure;
+    int32_t tonemapping;
+    int32_t srgb_transform;
+    float   midpoint;
+    float   contrast;
+} bpt_post_settings;
+/* film -> 0xAARRGGBB pixels exactly as the display loop does: NaN -> cyan, /w, max(0), 2^exposure, 1-exp(-x),
+ * pow(x, 1/2.23333), sigmoidal contrast, *255, + TPDF dither from an RGB8 blue-noise tile (power-of-two w/h; NULL
+ * skips the dither term), clamp, pack.  out = w*h uint32 on the host. */
+BPT_API int bpt_resolve_bgra8(bpt_ctx* ctx, const bpt_post_settings* post, const uint8_t* dither_rgb8,
+                              uint32_t dither_w, uint32_t dither_h, uint32_t* out_pixels);
+/* write_bitmap (assets.cpp:693-724): 32-bit top-down BMP, byte-identical header. Host only. */
+BPT_API int bpt_write_bitmap(const char* file_name, const uint32_t* pixels, uint32_t w, uint32_t h);
+
 /* Parity / diagnostics. */
 BPT_API int bpt_trace(bpt_ctx* ctx, uint32_t n, const bpt_ray* rays, int mode, uint32_t ignored_primitive,
                       bpt_hit* out_hits);
