@@ -323,9 +323,12 @@ struct ShadowSrc {         // NEE shadow rays; an unoccluded ray releases its pe
     }
 };
 
+#ifndef BPT_TRACE_MIN_CTAS
+#define BPT_TRACE_MIN_CTAS 7
+#endif
 // intersect_scene for every active path (integrators.cpp:615).  in_queue == nullptr means "slot = i".
 template <bool STATS>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, BPT_TRACE_MIN_CTAS)
 k_trace_closest(DScene sc, DPathState st, const uint32_t* __restrict__ in_queue, const uint32_t* __restrict__ n_ptr,
                 uint32_t n_fixed, uint32_t* cursor, uint32_t refill, DStats* stats) {
     uint32_t n = n_ptr ? *n_ptr : n_fixed;
@@ -337,7 +340,7 @@ k_trace_closest(DScene sc, DPathState st, const uint32_t* __restrict__ in_queue,
 
 // intersect_shadow_ray for every queued NEE sample (integrators.cpp:756)
 template <bool STATS>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, BPT_TRACE_MIN_CTAS)
 k_trace_shadow(DScene sc, DPathState st, const DShadowItem* __restrict__ items, const uint32_t* __restrict__ n_ptr,
                uint32_t* cursor, uint32_t refill, DStats* stats) {
     uint32_t n = *n_ptr;
@@ -360,7 +363,10 @@ BPT_D uint32_t queue_append(uint32_t* counter, bool want) {
 }
 
 // One bounce of advanced_integrator (integrators.cpp:612-818) for every active path.
-__global__ void __launch_bounds__(128)
+#ifndef BPT_SHADE_MIN_CTAS
+#define BPT_SHADE_MIN_CTAS 8      // 64 registers: measured 14.7 ms vs 18.6 ms at 4 CTAs/128 registers on C2 (latency-bound on path state)
+#endif
+__global__ void __launch_bounds__(128, BPT_SHADE_MIN_CTAS)
 k_shade(DScene sc, DPathState st, BatchDesc b, uint32_t bounce,
         const uint32_t* __restrict__ in_queue, const uint32_t* __restrict__ n_ptr, uint32_t n_fixed,
         uint32_t* __restrict__ out_queue, uint32_t* out_count,

@@ -24,7 +24,7 @@ class BptError(RuntimeError):
 
 
 def library_path():
-    return os.path.join(HERE, "libbpt.so")
+    return os.environ.get("BPT_LIBRARY") or os.path.join(HERE, "libbpt.so")
 
 
 def build_library(force=False):
