@@ -304,7 +304,7 @@ def main():
         h2d, d2h = r2.transfer_bytes(reset=True)
         e2e = {"value": rays_all / dt / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": h2d // n_e2e,
                "d2h_bytes_per_step": d2h // n_e2e, "ms_per_step": dt * 1e3,
-               "what": "bpt_upload_scene (flatten + H2D of the whole scene) + bpt_render_pass + bpt_download_film per step"}
+               "what": "per step: bpt_upload_scene (whole scene from page-locked host memory, re-laid-out on the device) + bpt_render_pass + bpt_download_film to a host array"}
 
     if rank != 0:
         if dist is not None:

@@ -19,6 +19,9 @@ using namespace bpt;
 
 namespace {
 
+enum SceneSlot { SL_MATERIALS, SL_PRIMITIVES, SL_PLANES, SL_MESHES, SL_LIGHTS, SL_TLAS_NODES, SL_TLAS_INDICES, SL_BLAS_NODES,
+                 SL_TRIANGLES, SL_TRI_ORIGINAL, SL_RAW_TRIANGLES, SL_NORMALS, SL_RAW_NORMALS, SL_SKYDOME, SL_RAW_SKYDOME };
+
 enum Stage { ST_RAYGEN, ST_TRACE, ST_SHADE, ST_SHADOW, ST_SPLAT, ST_COUNT };
 
 struct TimedSpan { cudaEvent_t a, b; int stage; };
@@ -35,7 +38,10 @@ struct bpt_ctx {
     DScene sc{};
     bool scene_ready = false;
     bool tables_ready = false;
-    std::vector<void*> scene_allocs;      // freed on re-upload / destroy
+    std::vector<void*> scene_allocs;      // (unused, kept for destroy)
+    struct Slot { void* p = nullptr; size_t cap = 0; } slots[16];   // grow-only device buffers of the uploaded scene
+    char* staging = nullptr;              // pinned host block for the small flattened tables
+    size_t staging_capacity = 0;
     uint32_t* tri_original = nullptr;     // DTriangle slot -> original triangle index (MeshBVH::indices)
 
     uint8_t *d_perm = nullptr, *d_sobol = nullptr, *d_scramble = nullptr, *d_rank = nullptr;
@@ -89,6 +95,19 @@ int upload(bpt_ctx* ctx, const T* host, size_t count, const T** out, std::vector
     if (count) CK(cudaMemcpyAsync(d, host, count*sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
     ctx->h2d_bytes += count*sizeof(T);
     *out = (const T*)d;
+    return BPT_OK;
+}
+
+int device_slot(bpt_ctx* ctx, int id, size_t bytes, void** out) {
+    bpt_ctx::Slot& sl = ctx->slots[id];
+    bytes = std::max<size_t>(bytes, 256);
+    if (sl.cap < bytes) {
+        if (sl.p) cudaFree(sl.p);
+        sl.p = nullptr; sl.cap = 0;
+        CK(cudaMalloc(&sl.p, bytes));
+        sl.cap = bytes;
+    }
+    *out = sl.p;
     return BPT_OK;
 }
 
@@ -221,6 +240,8 @@ void bpt_destroy(bpt_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     free_all(&ctx->scene_allocs);
+    for (auto& sl : ctx->slots) if (sl.p) cudaFree(sl.p);
+    if (ctx->staging) cudaFreeHost(ctx->staging);
     for (auto& pp : ctx->pipes) {
         cudaStreamSynchronize(pp.stream);
         free_all(&pp.allocs);
@@ -273,59 +294,43 @@ int bpt_upload_scene(bpt_ctx* ctx, const bpt_scene* scene) {
     if (!ctx || !scene) { set_error("bpt_upload_scene: null argument"); return BPT_ERR_ARG; }
     if (!scene->has_tlas) { set_error("bpt_upload_scene: call bpt_create_scene_bvh first"); return BPT_ERR_STATE; }
     CK(cudaSetDevice(ctx->device));
-    CK(cudaStreamSynchronize(ctx->stream));
-    free_all(&ctx->scene_allocs);
+    CK(cudaStreamSynchronize(ctx->stream));          // nothing may still be traversing the previous scene
     ctx->scene_ready = false;
     DScene& sc = ctx->sc;
-    std::vector<void*>* own = &ctx->scene_allocs;
+    cudaStream_t s = ctx->stream;
 
-    // materials (+ the integrator's local "air", integrators.cpp:597-599)
-    std::vector<DMaterial> mats(scene->materials.size() + 1);
-    memset(mats.data(), 0, mats.size()*sizeof(DMaterial));
-    for (size_t i = 0; i < scene->materials.size(); ++i) memcpy(&mats[i], &scene->materials[i], sizeof(bpt_material));
-    mats.back().ior = 1.0f;
-    mats.back().is_participating_medium = 1;
-    if (mats.size() > 0xFFFF) { set_error("bpt_upload_scene: more than 65534 materials"); return BPT_ERR_UNSUPPORTED; }
-
-    // meshes: concatenate BLAS node arrays and leaf-ordered triangles
-    std::vector<DMesh> meshes(scene->meshes.size());
-    std::vector<bpt_bvh_node> blas_nodes;
-    std::vector<DTriangle> tris;
-    std::vector<float4> normals;
-    std::vector<uint32_t> tri_original;
-    bool any_normals = false;
-    for (const HostMesh& m : scene->meshes) any_normals |= m.has_normals;
-    for (size_t mi = 0; mi < scene->meshes.size(); ++mi) {
-        const HostMesh& m = scene->meshes[mi];
-        DMesh& dm = meshes[mi];
-        dm.node_base = (uint32_t)blas_nodes.size();
-        dm.tri_base = (uint32_t)tris.size();
-        dm.triangle_count = m.triangle_count;
-        dm.has_normals = m.has_normals ? 1u : 0u;
-        blas_nodes.insert(blas_nodes.end(), m.bvh.nodes.begin(), m.bvh.nodes.end());
-        if (blas_nodes.size() & 1) blas_nodes.emplace_back();     // keep sibling pairs 64-byte aligned
-        size_t base = tris.size();
-        tris.resize(base + m.triangle_count);
-        if (any_normals) normals.resize((base + m.triangle_count)*3, make_float4(0, 0, 0, 0));
-        tri_original.insert(tri_original.end(), m.bvh.indices.begin(), m.bvh.indices.end());
-        for (uint32_t i = 0; i < m.triangle_count; ++i) {
-            const float* p = &m.leaf_triangles[(size_t)i*9];
-            DTriangle& t = tris[base + i];
-            uint32_t orig = m.bvh.indices[i];
-            float orig_bits; memcpy(&orig_bits, &orig, 4);
-            t.a_idx = make_float4(p[0], p[1], p[2], orig_bits);
-            t.e1 = make_float4(p[3] - p[0], p[4] - p[1], p[5] - p[2], 0.0f);     // edge1 = b - a (intersection.cpp:145)
-            t.e2 = make_float4(p[6] - p[0], p[7] - p[1], p[8] - p[2], 0.0f);     // edge2 = c - a (:146)
-            if (m.has_normals) {
-                const float* nn = &m.normals[(size_t)orig*9];
-                for (int k = 0; k < 3; ++k) normals[(base + i)*3 + k] = make_float4(nn[k*3], nn[k*3 + 1], nn[k*3 + 2], 0.0f);
-            }
-        }
+    if (scene->materials.size() + 1 > 0xFFFF) { set_error("bpt_upload_scene: more than 65534 materials"); return BPT_ERR_UNSUPPORTED; }
+    for (uint32_t l : scene->lights) {
+        if (l >= scene->primitives.size()) { set_error("bpt_upload_scene: light id %u is not a primitive (emissive plane?)", l); return BPT_ERR_UNSUPPORTED; }
     }
 
-    std::vector<DPrimitive> prims(scene->primitives.size());
-    memset(prims.data(), 0, prims.size()*sizeof(DPrimitive));
-    for (size_t i = 0; i < scene->primitives.size(); ++i) {
+    // Small tables are flattened on the host into one pinned staging block; the big arrays (BLAS nodes, leaf-ordered
+    // triangles, indices, normals, skydome) already live in page-locked memory inside the host scene (PinnedVec) and go to
+    // the device as they are; the 48-byte DTriangle records and float4 texels are then built by kernels on the device.
+    size_t n_mats = scene->materials.size() + 1, n_prims = scene->primitives.size(), n_planes = scene->planes.size(),
+           n_meshes = scene->meshes.size(), n_lights = scene->lights.size();
+    size_t small_bytes = n_mats*sizeof(DMaterial) + n_prims*sizeof(DPrimitive) + n_planes*sizeof(DPlane) + n_meshes*sizeof(DMesh) + 1024;
+    if (ctx->staging_capacity < small_bytes) {
+        if (ctx->staging) cudaFreeHost(ctx->staging);
+        ctx->staging = nullptr; ctx->staging_capacity = 0;
+        CK(cudaHostAlloc((void**)&ctx->staging, small_bytes*2, cudaHostAllocDefault));
+        ctx->staging_capacity = small_bytes*2;
+    }
+    char* stage = ctx->staging;
+    auto carve = [&](size_t bytes) { char* p = stage; stage += (bytes + 255) & ~(size_t)255; return p; };
+    DMaterial* mats = (DMaterial*)carve(n_mats*sizeof(DMaterial));
+    DPrimitive* prims = (DPrimitive*)carve(n_prims*sizeof(DPrimitive));
+    DPlane* planes = (DPlane*)carve(n_planes*sizeof(DPlane));
+    DMesh* meshes = (DMesh*)carve(n_meshes*sizeof(DMesh));
+
+    // materials (+ the integrator's local "air", integrators.cpp:597-599)
+    memset(mats, 0, n_mats*sizeof(DMaterial));
+    for (size_t i = 0; i + 1 < n_mats; ++i) memcpy(&mats[i], &scene->materials[i], sizeof(bpt_material));
+    mats[n_mats - 1].ior = 1.0f;
+    mats[n_mats - 1].is_participating_medium = 1;
+
+    memset(prims, 0, n_prims*sizeof(DPrimitive));
+    for (size_t i = 0; i < n_prims; ++i) {
         const HostPrimitive& hp = scene->primitives[i];
         DPrimitive& dp = prims[i];
         const bpt_m4x4inv& xf = hp.transform >= 0 ? scene->transforms[hp.transform] : identity_transform();
@@ -335,68 +340,90 @@ int bpt_upload_scene(bpt_ctx* ctx, const bpt_scene* scene) {
         dp.sphere_r = hp.sphere_r;
         memcpy(dp.box_r, hp.box_r, 12);
     }
-    std::vector<DPlane> planes(scene->planes.size());
-    memset(planes.data(), 0, planes.size()*sizeof(DPlane));
-    for (size_t i = 0; i < scene->planes.size(); ++i) {
+    memset(planes, 0, n_planes*sizeof(DPlane));
+    for (size_t i = 0; i < n_planes; ++i) {
         memcpy(planes[i].n, scene->planes[i].plane_n, 12);
         planes[i].d = scene->planes[i].plane_d;
         planes[i].material = scene->planes[i].material;
     }
-    for (uint32_t l : scene->lights) {
-        if (l >= scene->primitives.size()) { set_error("bpt_upload_scene: light id %u is not a primitive (emissive plane?)", l); return BPT_ERR_UNSUPPORTED; }
-    }
 
-    // FMNMX slab test precondition (trace.cuh make_ray): all node boxes finite and inside 1e15
-    bool tame = true;
-    auto check_nodes = [&](const std::vector<bpt_bvh_node>& nodes) {
-        for (const bpt_bvh_node& nd : nodes)
-            for (int k = 0; k < 3; ++k) {
-                float ext = fabsf(nd.bv_p[k]) + fabsf(nd.bv_r[k]);
-                if (!(ext < 1e15f)) {
-                    // the empty-scene root has bv_r = -inf by construction (it can never be hit); anything else disables the fast path
-                    tame = false;
-                }
-            }
-    };
-    check_nodes(scene->tlas.nodes);
-    check_nodes(blas_nodes);
+    // mesh directory + totals; FMNMX slab-test precondition (trace.cuh make_ray): all node boxes inside 1e15
+    size_t total_nodes = 0, total_tris = 0;
+    bool any_normals = false;
+    bool tame = scene->tlas.max_abs_extent < 1e15f || scene->tlas.indices.empty();
+    for (size_t mi = 0; mi < n_meshes; ++mi) {
+        const HostMesh& m = scene->meshes[mi];
+        meshes[mi].node_base = (uint32_t)total_nodes;
+        meshes[mi].tri_base = (uint32_t)total_tris;
+        meshes[mi].triangle_count = m.triangle_count;
+        meshes[mi].has_normals = m.has_normals ? 1u : 0u;
+        total_nodes += (m.bvh.nodes.size() + 1) & ~(size_t)1;      // keep sibling pairs 64-byte aligned
+        total_tris += m.triangle_count;
+        any_normals |= m.has_normals;
+        tame = tame && (m.bvh.max_abs_extent < 1e15f);
+    }
     sc.tame_bounds = tame ? 1u : 0u;
 
-    int rc = 0;
-    const bpt_bvh_node* d_tlas = nullptr; const bpt_bvh_node* d_blas = nullptr;
-    rc |= upload(ctx, scene->tlas.nodes.data(), scene->tlas.nodes.size(), &d_tlas, own);
-    rc |= upload(ctx, scene->tlas.indices.data(), scene->tlas.indices.size(), &sc.tlas_indices, own);
-    rc |= upload(ctx, blas_nodes.data(), blas_nodes.size(), &d_blas, own);
-    rc |= upload(ctx, tris.data(), tris.size(), &sc.triangles, own);
-    rc |= upload(ctx, meshes.data(), meshes.size(), &sc.meshes, own);
-    rc |= upload(ctx, prims.data(), prims.size(), &sc.primitives, own);
-    rc |= upload(ctx, planes.data(), planes.size(), &sc.planes, own);
-    rc |= upload(ctx, mats.data(), mats.size(), &sc.materials, own);
-    rc |= upload(ctx, scene->lights.data(), scene->lights.size(), &sc.lights, own);
-    const uint32_t* d_orig = nullptr;
-    rc |= upload(ctx, tri_original.data(), tri_original.size(), &d_orig, own);
+    void* d = nullptr;
+    #define SLOT(id, bytes) do { int rc_ = device_slot(ctx, id, (bytes), &d); if (rc_) return rc_; } while (0)
+    #define H2D(dst, src, bytes) do { if ((bytes) > 0) { CK(cudaMemcpyAsync((dst), (src), (bytes), cudaMemcpyHostToDevice, s)); ctx->h2d_bytes += (bytes); } } while (0)
+    SLOT(SL_MATERIALS, n_mats*sizeof(DMaterial));   sc.materials = (const DMaterial*)d;   H2D(d, mats, n_mats*sizeof(DMaterial));
+    SLOT(SL_PRIMITIVES, n_prims*sizeof(DPrimitive)); sc.primitives = (const DPrimitive*)d; H2D(d, prims, n_prims*sizeof(DPrimitive));
+    SLOT(SL_PLANES, n_planes*sizeof(DPlane));       sc.planes = (const DPlane*)d;         H2D(d, planes, n_planes*sizeof(DPlane));
+    SLOT(SL_MESHES, n_meshes*sizeof(DMesh));        sc.meshes = (const DMesh*)d;          H2D(d, meshes, n_meshes*sizeof(DMesh));
+    SLOT(SL_LIGHTS, n_lights*sizeof(uint32_t));     sc.lights = (const uint32_t*)d;       H2D(d, scene->lights.data(), n_lights*sizeof(uint32_t));
+    SLOT(SL_TLAS_NODES, scene->tlas.nodes.size()*sizeof(bpt_bvh_node)); sc.tlas_nodes = (const DNodeHalf*)d;
+    H2D(d, scene->tlas.nodes.data(), scene->tlas.nodes.size()*sizeof(bpt_bvh_node));
+    SLOT(SL_TLAS_INDICES, scene->tlas.indices.size()*sizeof(uint32_t)); sc.tlas_indices = (const uint32_t*)d;
+    H2D(d, scene->tlas.indices.data(), scene->tlas.indices.size()*sizeof(uint32_t));
+
+    SLOT(SL_BLAS_NODES, total_nodes*sizeof(bpt_bvh_node)); bpt_bvh_node* d_blas = (bpt_bvh_node*)d; sc.blas_nodes = (const DNodeHalf*)d;
+    SLOT(SL_TRIANGLES, total_tris*sizeof(DTriangle));      DTriangle* d_tris = (DTriangle*)d;       sc.triangles = d_tris;
+    SLOT(SL_TRI_ORIGINAL, total_tris*sizeof(uint32_t));    uint32_t* d_orig = (uint32_t*)d;         ctx->tri_original = d_orig;
+    SLOT(SL_RAW_TRIANGLES, total_tris*9*sizeof(float));    float* d_raw = (float*)d;
+    float4* d_normals = nullptr; float* d_raw_normals = nullptr;
     sc.normals = nullptr;
-    if (any_normals) rc |= upload(ctx, normals.data(), normals.size(), &sc.normals, own);
+    if (any_normals) {
+        SLOT(SL_NORMALS, total_tris*3*sizeof(float4));     d_normals = (float4*)d; sc.normals = d_normals;
+        SLOT(SL_RAW_NORMALS, total_tris*9*sizeof(float));  d_raw_normals = (float*)d;
+    }
+    for (size_t mi = 0; mi < n_meshes; ++mi) {
+        const HostMesh& m = scene->meshes[mi];
+        size_t nb = meshes[mi].node_base, tb = meshes[mi].tri_base, nt = m.triangle_count;
+        H2D(d_blas + nb, m.bvh.nodes.data(), m.bvh.nodes.size()*sizeof(bpt_bvh_node));
+        if (m.bvh.nodes.size() & 1) CK(cudaMemsetAsync(d_blas + nb + m.bvh.nodes.size(), 0, sizeof(bpt_bvh_node), s));
+        H2D(d_raw + tb*9, m.leaf_triangles.data(), nt*9*sizeof(float));
+        H2D(d_orig + tb, m.bvh.indices.data(), nt*sizeof(uint32_t));
+        if (m.has_normals) H2D(d_raw_normals + tb*9, m.normals.data(), nt*9*sizeof(float));
+        k_build_triangles<<<grid_for(ctx, nt, 256, 8), 256, 0, s>>>(d_raw + tb*9, d_orig + tb, (uint32_t)nt, d_tris + tb,
+                                                                    m.has_normals ? d_raw_normals + tb*9 : nullptr,
+                                                                    d_normals ? d_normals + tb*3 : nullptr);
+        ctx->total_launches += 1;
+    }
+
     sc.skydome = nullptr; sc.skydome_w = sc.skydome_h = 0;
     if (!scene->skydome.empty()) {
-        std::vector<float4> sky((size_t)scene->skydome_w*scene->skydome_h);
-        for (size_t i = 0; i < sky.size(); ++i) sky[i] = make_float4(scene->skydome[i*3], scene->skydome[i*3 + 1], scene->skydome[i*3 + 2], 0.0f);
-        rc |= upload(ctx, sky.data(), sky.size(), &sc.skydome, own);
+        size_t texels = (size_t)scene->skydome_w*scene->skydome_h;
+        SLOT(SL_RAW_SKYDOME, texels*3*sizeof(float)); float* d_raw_sky = (float*)d;
+        SLOT(SL_SKYDOME, texels*sizeof(float4));      float4* d_sky = (float4*)d;
+        H2D(d_raw_sky, scene->skydome.data(), texels*3*sizeof(float));
+        k_expand_rgb<<<grid_for(ctx, texels, 256, 8), 256, 0, s>>>(d_raw_sky, (uint32_t)texels, d_sky);
+        ctx->total_launches += 1;
+        sc.skydome = d_sky;
         sc.skydome_w = scene->skydome_w; sc.skydome_h = scene->skydome_h;
     }
-    if (rc) return BPT_ERR_CUDA;
-    sc.tlas_nodes = (const DNodeHalf*)d_tlas;
-    sc.blas_nodes = (const DNodeHalf*)d_blas;
-    ctx->tri_original = (uint32_t*)d_orig;
-    sc.plane_count = (uint32_t)planes.size();
-    sc.primitive_count = (uint32_t)prims.size();
+    #undef SLOT
+    #undef H2D
+    sc.plane_count = (uint32_t)n_planes;
+    sc.primitive_count = (uint32_t)n_prims;
     sc.material_count = (uint32_t)scene->materials.size();
     sc.air_material = sc.material_count;
-    sc.light_count = (uint32_t)scene->lights.size();
+    sc.light_count = (uint32_t)n_lights;
 
-    rc = bpt_update_settings(ctx, scene);
+    int rc = bpt_update_settings(ctx, scene);
     if (rc) return rc;
     CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaGetLastError());
     ctx->scene_ready = true;
     return BPT_OK;
 }

@@ -194,8 +194,14 @@ void build_bvh_sah_binned(std::vector<SortEntry>& entries, HostBVH* out) {
         }
     }
 
-    nodes.resize(node_count);
-    out->nodes.swap(nodes);
+    out->nodes.assign(nodes.begin(), nodes.begin() + node_count);
+    float ext = 0.0f;
+    for (uint32_t i = 0; i < node_count; ++i)
+        for (int k = 0; k < 3; ++k) {
+            float e = fabsf(nodes[i].bv_p[k]) + fabsf(nodes[i].bv_r[k]);
+            if (!(e <= ext)) ext = e;          // NaN sticks
+        }
+    out->max_abs_extent = ext;
     out->indices.resize(n);
     for (uint32_t i = 0; i < n; ++i) out->indices[i] = entries[i].index;
 }

@@ -3,8 +3,11 @@
 // (:26-59, :164-185, :1424-1453); all of it is re-implemented against an index-based model (host_scene.h).
 #include "host_scene.h"
 
+#include <cuda_runtime.h>
 #include <float.h>
 #include <math.h>
+#include <mutex>
+#include <set>
 #include <stdarg.h>
 #include <stdio.h>
 #include <string.h>
@@ -18,6 +21,33 @@ void set_error(const char* fmt, ...) {
     va_start(args, fmt);
     vsnprintf(g_error, sizeof(g_error), fmt, args);
     va_end(args);
+}
+
+namespace {
+std::mutex g_pin_mutex;
+std::set<void*> g_malloced;     // blocks that came from malloc because cudaHostAlloc was unavailable
+}
+
+void* pinned_alloc(size_t bytes) {
+    if (bytes == 0) bytes = 1;
+    void* p = nullptr;
+    if (bytes >= (1u << 16) && cudaHostAlloc(&p, bytes, cudaHostAllocDefault) == cudaSuccess && p) return p;
+    cudaGetLastError();             // clear "no driver" etc.; small blocks are not worth pinning
+    p = malloc(bytes);
+    if (!p) throw std::bad_alloc();
+    std::lock_guard<std::mutex> lock(g_pin_mutex);
+    g_malloced.insert(p);
+    return p;
+}
+
+void pinned_free(void* p) {
+    if (!p) return;
+    {
+        std::lock_guard<std::mutex> lock(g_pin_mutex);
+        auto it = g_malloced.find(p);
+        if (it != g_malloced.end()) { g_malloced.erase(it); free(p); return; }
+    }
+    cudaFreeHost(p);
 }
 
 const bpt_m4x4inv& identity_transform() {

@@ -12,18 +12,36 @@
 
 namespace bpt {
 
+// Page-locked host memory for the arrays bpt_upload_scene() copies to the device (so the H2D copies run at PCIe speed
+// and asynchronously).  Falls back to malloc when no CUDA driver is present (host-only use, e.g. the CPU test suite).
+void* pinned_alloc(size_t bytes);
+void  pinned_free(void* p);
+
+template <class T>
+struct PinnedAllocator {
+    typedef T value_type;
+    PinnedAllocator() {}
+    template <class U> PinnedAllocator(const PinnedAllocator<U>&) {}
+    T* allocate(size_t n) { return (T*)pinned_alloc(n*sizeof(T)); }
+    void deallocate(T* p, size_t) { pinned_free(p); }
+    template <class U> bool operator==(const PinnedAllocator<U>&) const { return true; }
+    template <class U> bool operator!=(const PinnedAllocator<U>&) const { return false; }
+};
+template <class T> using PinnedVec = std::vector<T, PinnedAllocator<T>>;
+
 struct HostBVH {
-    std::vector<bpt_bvh_node> nodes;     // bit-identical to BVH::nodes[0..node_count) (bvh.h:39-45)
-    std::vector<uint32_t>     indices;   // BVH::indices
+    PinnedVec<bpt_bvh_node> nodes;       // bit-identical to BVH::nodes[0..node_count) (bvh.h:39-45)
+    PinnedVec<uint32_t>     indices;     // BVH::indices
+    float max_abs_extent = 0.0f;         // max over nodes/axes of |bv_p| + |bv_r| (NaN/inf propagate): FMNMX slab-test precondition
 };
 
 struct HostMesh {
     uint32_t triangle_count = 0;
     bool     has_normals = false;
     std::vector<float> positions;        // 9 floats per triangle, caller order (Mesh::triangles)
-    std::vector<float> normals;          // 9 floats per triangle, caller order (get_normals(mesh))
+    PinnedVec<float> normals;            // 9 floats per triangle, caller order (get_normals(mesh))
     HostBVH  bvh;                        // MeshBVH (bvh.h:52-58), BVHStorage_Scalar
-    std::vector<float> leaf_triangles;   // MeshBVH::triangles: positions re-ordered into leaf order
+    PinnedVec<float> leaf_triangles;     // MeshBVH::triangles: positions re-ordered into leaf order
 };
 
 struct HostPrimitive {                   // Primitive (primitives.h:92-106) without pointers
@@ -52,7 +70,7 @@ struct bpt_scene {
     float top_sky_color[3] = {0, 0, 0};
     float bot_sky_color[3] = {0, 0, 0};
     uint32_t skydome_w = 0, skydome_h = 0;
-    std::vector<float> skydome;          // w*h*3
+    bpt::PinnedVec<float> skydome;       // w*h*3
 
     bpt_camera   new_camera{};           // Scene::new_camera (what the user edits)
     bpt_settings new_settings{};         // Scene::new_settings

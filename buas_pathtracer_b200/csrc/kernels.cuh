@@ -818,6 +818,33 @@ __global__ void k_resolve(const float4* __restrict__ film, uint32_t w, uint32_t 
     }
 }
 
+// upload-time re-layout on the device: leaf-ordered 36-byte triangles -> 48-byte {a, idx}{b-a}{c-a} records (the two
+// edge subtractions are the first operations of ray_intersect_triangle, intersection.cpp:145-146: same IEEE ops, done
+// once here), and caller-order vertex normals -> leaf order.
+__global__ void k_build_triangles(const float* __restrict__ raw, const uint32_t* __restrict__ original, uint32_t n,
+                                  DTriangle* __restrict__ out, const float* __restrict__ raw_normals, float4* __restrict__ out_normals) {
+    for (uint32_t i = blockIdx.x*blockDim.x + threadIdx.x; i < n; i += gridDim.x*blockDim.x) {
+        const float* p = raw + (size_t)i*9;
+        uint32_t orig = original[i];
+        DTriangle t;
+        t.a_idx = make_float4(p[0], p[1], p[2], __uint_as_float(orig));
+        t.e1 = make_float4(p[3] - p[0], p[4] - p[1], p[5] - p[2], 0.0f);
+        t.e2 = make_float4(p[6] - p[0], p[7] - p[1], p[8] - p[2], 0.0f);
+        out[i] = t;
+        if (raw_normals) {
+            const float* nn = raw_normals + (size_t)orig*9;
+            out_normals[(size_t)i*3 + 0] = make_float4(nn[0], nn[1], nn[2], 0.0f);
+            out_normals[(size_t)i*3 + 1] = make_float4(nn[3], nn[4], nn[5], 0.0f);
+            out_normals[(size_t)i*3 + 2] = make_float4(nn[6], nn[7], nn[8], 0.0f);
+        }
+    }
+}
+
+__global__ void k_expand_rgb(const float* __restrict__ rgb, uint32_t n, float4* __restrict__ out) {
+    for (uint32_t i = blockIdx.x*blockDim.x + threadIdx.x; i < n; i += gridDim.x*blockDim.x)
+        out[i] = make_float4(rgb[(size_t)i*3], rgb[(size_t)i*3 + 1], rgb[(size_t)i*3 + 2], 0.0f);
+}
+
 __global__ void k_reset_counters(uint32_t* counters, int which_mask) {
     if (threadIdx.x < 8 && (which_mask >> threadIdx.x) & 1) counters[threadIdx.x] = 0;
 }
