@@ -22,9 +22,9 @@ def test_row_partition_covers_frame_once():
                     assert 0 <= y0 < y1 <= h
                     cover[y0:y1] += 1
             assert np.all(cover == 1)
-            if world > 1 and h >= 64 * world:
+            if world > 1 and h >= bench.BLOCK_ROWS * world:
                 sizes = [sum(y1 - y0 for y0, y1 in bench.my_rows(h, r, world)) for r in range(world)]
-                assert max(sizes) - min(sizes) <= 64 + h % 64
+                assert max(sizes) - min(sizes) <= bench.BLOCK_ROWS + h % bench.BLOCK_ROWS
 
 
 def _worker(rank, world, port, out):
