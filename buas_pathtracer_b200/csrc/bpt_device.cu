@@ -64,6 +64,7 @@ struct bpt_ctx {
         uint64_t d_record_capacity = 0;
     } pipes[2];
     int n_pipes = 2;
+    bool merge_traces = true;             // trace bounce b's extension rays and bounce b-1's shadow rays in one launch
     int32_t* d_row_map = nullptr;
     uint32_t row_map_capacity = 0;
 
@@ -227,6 +228,7 @@ int bpt_create(int device, bpt_ctx** out_ctx) {
         if (m > 0) ctx->trace_ctas_per_sm = m;
     }
     if (const char* e = getenv("BPT_REFILL")) { int v = atoi(e); if (v >= 1 && v <= 33) ctx->refill = (uint32_t)v; }
+    if (const char* e = getenv("BPT_MERGE_TRACES")) ctx->merge_traces = atoi(e) != 0;
     if (const char* e = getenv("BPT_PIPES")) { int v = atoi(e); if (v >= 1 && v <= 2) ctx->n_pipes = v; }
     if (const char* e = getenv("BPT_TRACE_CTAS")) { int v = atoi(e); if (v >= 1 && v <= 32) ctx->trace_ctas_per_sm = v; }
     const char* dt = getenv("BPT_DETAILED_TIMING");
@@ -577,6 +579,11 @@ retry_shape:
     S = (uint32_t)std::min<uint64_t>(spp, std::max<uint64_t>(1, cap / rect_w));
     rows_per_batch = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(rect_h, cap / ((uint64_t)rect_w*S)));
     n_batches = (uint64_t)((spp + S - 1)/S) * ((rect_h + rows_per_batch - 1)/rows_per_batch);
+    if (n_batches == 1 && n_pipes == 2 && S == spp && rect_h >= 2 && (uint64_t)rect_w*rect_h*spp >= (2ull << 20)) {
+        // a single batch cannot overlap with anything: split it so the two pipelines hide each other's kernel tails
+        rows_per_batch = (rect_h + 1)/2;
+        n_batches = 2;
+    }
     if (n_batches < (uint64_t)n_pipes) n_pipes = 1;
     if (n_pipes == 2 && ((rect_h + rows_per_batch - 1)/rows_per_batch) & 1) {
         // even out the last pair of batches
@@ -647,33 +654,46 @@ retry_shape:
             ctx->launches++;
 
             uint32_t* counters = pp.q.counters;
+            // Per bounce b:  trace { extension rays of b  +  shadow rays queued by bounce b-1 }  ->  shade b.
+            // counters: [0]/[1] = active-queue sizes (ping-pong), [2] = shadow count, [3] = fetch cursor.
+            // With the counting instantiations (stats) the two populations are traced by separate launches.
+            // (also when per-kernel timing is requested, so that each kernel's own duration is what gets measured)
+            const bool merged = !stats && !ctx->detailed_timing && ctx->merge_traces;
             for (uint32_t bounce = 0; bounce < max_bounce; ++bounce) {
                 int in = bounce & 1, out = in ^ 1;
-                // counters: [in] = active count for this bounce (bounce 0 uses the identity queue), [out] and [2] (shadow) reset
                 const uint32_t* in_queue = bounce == 0 ? nullptr : pp.q.active[in];
                 const uint32_t* in_count = bounce == 0 ? nullptr : counters + in;
-                k_reset_counters<<<1, 32, 0, s>>>(counters, (1 << out) | (1 << 2) | (1 << 3) | (1 << 4));
-                ctx->launches++;
-                uint32_t work = b.slots;    // upper bound; kernels read the true count on the device
-
-                begin_span(ctx, ST_TRACE, s);
+                uint32_t work = b.slots;    // upper bound; kernels read the true counts on the device
                 uint32_t tg = grid_for(ctx, work, 128, ctx->trace_ctas_per_sm);
-                if (stats) k_trace_closest<true ><<<tg, 128, 0, s>>>(sc, pp.st, in_queue, in_count, b.slots, counters + 3, ctx->refill, ctx->d_stats);
-                else       k_trace_closest<false><<<tg, 128, 0, s>>>(sc, pp.st, in_queue, in_count, b.slots, counters + 3, ctx->refill, ctx->d_stats);
+
+                k_reset_counters<<<1, 32, 0, s>>>(counters, (1 << 3) | (1 << 4));
+                ctx->launches++;
+                begin_span(ctx, ST_TRACE, s);
+                if (merged && bounce > 0) {
+                    k_trace_merged<<<tg, 128, 0, s>>>(sc, pp.st, in_queue, in_count, pp.q.shadow, counters + 2, counters + 3, ctx->refill);
+                } else {
+                    if (stats) k_trace_closest<true ><<<tg, 128, 0, s>>>(sc, pp.st, in_queue, in_count, b.slots, counters + 3, ctx->refill, ctx->d_stats);
+                    else       k_trace_closest<false><<<tg, 128, 0, s>>>(sc, pp.st, in_queue, in_count, b.slots, counters + 3, ctx->refill, ctx->d_stats);
+                }
                 end_span(ctx, s);
                 ctx->launches++; ctx->trace_launches++;
 
+                // the shadow items of the previous bounce are consumed (merged) or not yet produced: reset before shading
+                k_reset_counters<<<1, 32, 0, s>>>(counters, (1 << out) | (1 << 2));
+                ctx->launches++;
                 begin_span(ctx, ST_SHADE, s);
                 k_shade<<<grid_for(ctx, work, 128, 16), 128, 0, s>>>(sc, pp.st, b, bounce, in_queue, in_count, b.slots,
                                                                     pp.q.active[out], counters + out, pp.q.shadow, counters + 2, ctx->d_stats);
                 end_span(ctx, s);
                 ctx->launches++;
 
-                begin_span(ctx, ST_SHADOW, s);
-                if (stats) k_trace_shadow<true ><<<tg, 128, 0, s>>>(sc, pp.st, pp.q.shadow, counters + 2, counters + 4, ctx->refill, ctx->d_stats);
-                else       k_trace_shadow<false><<<tg, 128, 0, s>>>(sc, pp.st, pp.q.shadow, counters + 2, counters + 4, ctx->refill, ctx->d_stats);
-                end_span(ctx, s);
-                ctx->launches++; ctx->trace_launches++;
+                if (!merged || bounce + 1 == max_bounce) {
+                    begin_span(ctx, ST_SHADOW, s);
+                    if (stats) k_trace_shadow<true ><<<tg, 128, 0, s>>>(sc, pp.st, pp.q.shadow, counters + 2, counters + 4, ctx->refill, ctx->d_stats);
+                    else       k_trace_shadow<false><<<tg, 128, 0, s>>>(sc, pp.st, pp.q.shadow, counters + 2, counters + 4, ctx->refill, ctx->d_stats);
+                    end_span(ctx, s);
+                    ctx->launches++; ctx->trace_launches++;
+                }
             }
 
             begin_span(ctx, ST_SPLAT, s);

@@ -289,14 +289,19 @@ BPT_D void flush_ray_counts(DStats* stats, uint32_t rays, uint32_t shadow) {
     }
 }
 
+#ifndef BPT_TRACE_MIN_CTAS
+#define BPT_TRACE_MIN_CTAS 7
+#endif
+
 struct ClosestSrc {        // rays come from the path state (through the active queue), hits go back to it
     DPathState st;
     const uint32_t* queue;
     bool store_w;
-    BPT_D void load(uint32_t i, V3& o, V3& d, float& max_t, uint32_t& ignored) const {
+    BPT_D void load(uint32_t i, V3& o, V3& d, float& max_t, uint32_t& ignored, bool& occ) const {
         uint32_t slot = queue ? queue[i] : i;
         float4 ro = st.ray_o[slot], rd = st.ray_d[slot];
         o = v3(ro); d = v3(rd); max_t = ro.w; ignored = 0u;       // intersect_scene passes PrimitiveID 0 (intersection.cpp:608)
+        occ = false;
     }
     BPT_D void store(uint32_t i, const HitRecord& h) const {
         uint32_t slot = queue ? queue[i] : i;
@@ -308,9 +313,10 @@ struct ClosestSrc {        // rays come from the path state (through the active 
 struct ShadowSrc {         // NEE shadow rays; an unoccluded ray releases its pending contribution (integrators.cpp:756-769)
     DPathState st;
     const DShadowItem* items;
-    BPT_D void load(uint32_t i, V3& o, V3& d, float& max_t, uint32_t& ignored) const {
+    BPT_D void load(uint32_t i, V3& o, V3& d, float& max_t, uint32_t& ignored, bool& occ) const {
         float4 ro = items[i].o_maxt, rd = items[i].d_light;
         o = v3(ro); d = v3(rd); max_t = ro.w; ignored = __float_as_uint(rd.w);
+        occ = true;
     }
     BPT_D void store(uint32_t i, const HitRecord& h) const {
         if (h.prim == BPT_HIT_MISS) {
@@ -323,9 +329,35 @@ struct ShadowSrc {         // NEE shadow rays; an unoccluded ray releases its pe
     }
 };
 
-#ifndef BPT_TRACE_MIN_CTAS
-#define BPT_TRACE_MIN_CTAS 7
-#endif
+// One launch for two ray populations: the extension rays of bounce b (closest hit) and the NEE shadow rays that
+// bounce b-1's shading queued.  Both are produced by the same k_shade launch and are independent of each other, so
+// tracing them together halves the number of traversal launches -- and with it the number of kernel tails, which are
+// set by the latency chain of the longest single ray and do not shrink with the batch (they cap multi-GPU scaling).
+// Closest-hit rays come first in the index space (they are the longer ones); shadow rays fill in behind them.
+struct MergedSrc {
+    ClosestSrc closest;
+    ShadowSrc shadow;
+    uint32_t n_closest;
+    BPT_D void load(uint32_t i, V3& o, V3& d, float& max_t, uint32_t& ignored, bool& occ) const {
+        if (i < n_closest) closest.load(i, o, d, max_t, ignored, occ);
+        else shadow.load(i - n_closest, o, d, max_t, ignored, occ);
+    }
+    BPT_D void store(uint32_t i, const HitRecord& h) const {
+        if (i < n_closest) closest.store(i, h);
+        else shadow.store(i - n_closest, h);
+    }
+};
+
+__global__ void __launch_bounds__(128, BPT_TRACE_MIN_CTAS)
+k_trace_merged(DScene sc, DPathState st, const uint32_t* __restrict__ in_queue, const uint32_t* __restrict__ n_closest_ptr,
+               const DShadowItem* __restrict__ items, const uint32_t* __restrict__ n_shadow_ptr,
+               uint32_t* cursor, uint32_t refill) {
+    uint32_t nc = *n_closest_ptr, ns = *n_shadow_ptr;
+    TraceCounters ctr = {};
+    MergedSrc src = {{st, in_queue, sc.normals != nullptr}, {st, items}, nc};
+    persistent_trace<TRACE_MODE_MIXED, false>(sc, src, nc + ns, cursor, refill, ctr);
+}
+
 // intersect_scene for every active path (integrators.cpp:615).  in_queue == nullptr means "slot = i".
 template <bool STATS>
 __global__ void __launch_bounds__(128, BPT_TRACE_MIN_CTAS)
@@ -334,7 +366,7 @@ k_trace_closest(DScene sc, DPathState st, const uint32_t* __restrict__ in_queue,
     uint32_t n = n_ptr ? *n_ptr : n_fixed;
     TraceCounters ctr = {};
     ClosestSrc src = {st, in_queue, sc.normals != nullptr};
-    persistent_trace<false, STATS>(sc, src, n, cursor, refill, ctr);
+    persistent_trace<TRACE_MODE_CLOSEST, STATS>(sc, src, n, cursor, refill, ctr);
     if (STATS) flush_counters(stats, ctr, false);
 }
 
@@ -346,7 +378,7 @@ k_trace_shadow(DScene sc, DPathState st, const DShadowItem* __restrict__ items, 
     uint32_t n = *n_ptr;
     TraceCounters ctr = {};
     ShadowSrc src = {st, items};
-    persistent_trace<true, STATS>(sc, src, n, cursor, refill, ctr);
+    persistent_trace<TRACE_MODE_OCCLUSION, STATS>(sc, src, n, cursor, refill, ctr);
     if (STATS) flush_counters(stats, ctr, true);
 }
 
@@ -721,9 +753,10 @@ struct ApiSrc {
     bpt_hit* out;
     const uint32_t* tri_original;
     uint32_t ignored;
-    BPT_D void load(uint32_t i, V3& o, V3& d, float& max_t, uint32_t& ign) const {
+    BPT_D void load(uint32_t i, V3& o, V3& d, float& max_t, uint32_t& ign, bool& occ) const {
         bpt_ray r = rays[i];
         o = v3(r.o); d = v3(r.d); max_t = r.max_t; ign = OCC ? ignored : 0u;
+        occ = OCC;
     }
     BPT_D void store(uint32_t i, const HitRecord& h) const {
         bpt_ray r = rays[i];
@@ -752,7 +785,7 @@ k_trace_api(DScene sc, const bpt_ray* __restrict__ rays, uint32_t n, uint32_t ig
             const uint32_t* __restrict__ tri_original, uint32_t* cursor, uint32_t refill, DStats* stats) {
     TraceCounters ctr = {};
     ApiSrc<OCC> src = {sc, rays, out, tri_original, ignored};
-    persistent_trace<OCC, STATS>(sc, src, n, cursor, refill, ctr);
+    persistent_trace<OCC ? TRACE_MODE_OCCLUSION : TRACE_MODE_CLOSEST, STATS>(sc, src, n, cursor, refill, ctr);
     if (STATS) flush_counters(stats, ctr, OCC);
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         atomicAdd(&stats->v[0], (unsigned long long)n);

@@ -157,7 +157,10 @@ struct TraversalStack {
     float    tn[BPT_STACK_DEPTH];
 };
 
-template <bool OCCLUSION, bool STATS>
+// MODE: 0 = closest hit (intersect_scene), 1 = occlusion (intersect_shadow_ray), 2 = per ray (Src::load says which)
+enum { TRACE_MODE_CLOSEST = 0, TRACE_MODE_OCCLUSION = 1, TRACE_MODE_MIXED = 2 };
+
+template <int MODE, bool STATS>
 struct Traversal {
     enum { S_NODE, S_ITEMS, S_POP, S_DONE };
 
@@ -170,6 +173,7 @@ struct Traversal {
     uint32_t cur_lf, cur_ca;
     uint32_t leaf_i, leaf_end;           // TLAS leaf items still to test
     uint32_t cur_prim, cur_tri_base, ignored;
+    bool occ;                            // TRACE_MODE_MIXED: this ray is a shadow ray
     const DNodeHalf* nodes;
     int sp, blas_sp, state, level;       // level: 0 = TLAS, 1 = inside a mesh BLAS
     uint32_t c_pops, c_inner, c_leaves;  // per intersect_mesh call; dropped on an occlusion early-out like g_stats
@@ -218,9 +222,9 @@ struct Traversal {
 // idle lanes are the largest group (and rays remain) they fetch new rays with one warp-aggregated atomicAdd and run
 // begin().  Every ray still performs exactly the reference's sequence of tests; only the interleaving between
 // independent rays changes.   Src supplies load(i, o, d, max_t, ignored) / store(i, hit).
-template <bool OCCLUSION, bool STATS, class Src>
+template <int MODE, bool STATS, class Src>
 BPT_D void persistent_trace(const DScene& sc, Src& src, uint32_t n, uint32_t* cursor, uint32_t refill, TraceCounters& ctr) {
-    typedef Traversal<OCCLUSION, STATS> TV;
+    typedef Traversal<MODE, STATS> TV;
     enum { P_IDLE = 0, P_INNER = 1, P_TRI = 2, P_ITEMS = 3 };
     const uint32_t FULL = 0xFFFFFFFFu;
     const uint32_t lane = threadIdx.x & 31u;
@@ -232,6 +236,8 @@ BPT_D void persistent_trace(const DScene& sc, Src& src, uint32_t n, uint32_t* cu
     bool exhausted = false;
     uint32_t my_index = 0;
     const bool tame = sc.tame_bounds != 0;
+    tv.occ = false;
+    auto occlusion = [&]() { return MODE == TRACE_MODE_MIXED ? tv.occ : (MODE == TRACE_MODE_OCCLUSION); };
 
     // after `tv.cur_*` changed: which phase does the lane wait for now
     auto classify = [&]() {
@@ -282,7 +288,9 @@ BPT_D void persistent_trace(const DScene& sc, Src& src, uint32_t n, uint32_t* cu
                 uint32_t idx = base + __popc(idle_mask & ((1u << lane) - 1u));
                 if (idx < n) {
                     V3 o, d; float max_t; uint32_t ign;
-                    src.load(idx, o, d, max_t, ign);
+                    bool is_occ = false;
+                    src.load(idx, o, d, max_t, ign, is_occ);
+                    tv.occ = is_occ;
                     my_index = idx;
                     tv.begin(sc, o, d, max_t, ign, ctr);
                     if (tv.done()) finish(); else classify();
@@ -332,7 +340,7 @@ BPT_D void persistent_trace(const DScene& sc, Src& src, uint32_t n, uint32_t* cu
                 if (triangle_test(tv.ray, v3(a), v3(e1), v3(e2), tv.t, tv.hit_v, tv.hit_w)) {
                     tv.hit_tri = slot;
                     tv.hit_prim = tv.cur_prim;
-                    if (OCCLUSION) { finish(); stop = true; }
+                    if (occlusion()) { finish(); stop = true; }
                 }
                 if (!stop && ++tri_k >= (tv.cur_ca & 0xFFFFu)) pop();
             }
@@ -354,12 +362,12 @@ BPT_D void persistent_trace(const DScene& sc, Src& src, uint32_t n, uint32_t* cu
                         if (type == BPT_PRIM_SPHERE) {
                             if (sphere_test(oray, __ldg(&prim->sphere_r), tv.t)) {
                                 tv.hit_prim = prim_index; tv.hit_tri = 0xFFFFFFFFu;
-                                if (OCCLUSION) finish();
+                                if (occlusion()) finish();
                             }
                         } else if (type == BPT_PRIM_BOX) {
                             if (box_test(oray, __ldg(&prim->box_r[0]), __ldg(&prim->box_r[1]), __ldg(&prim->box_r[2]), tv.t)) {
                                 tv.hit_prim = prim_index; tv.hit_tri = 0xFFFFFFFFu;
-                                if (OCCLUSION) finish();
+                                if (occlusion()) finish();
                             }
                         } else if (type == BPT_PRIM_MESH) {
                             const DMesh* mesh = sc.meshes + __ldg(&prim->mesh);

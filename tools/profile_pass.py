@@ -18,6 +18,7 @@ ap.add_argument("--h", type=int, default=0)
 ap.add_argument("--rows", type=str, default="")      # "y0:y1" sub-rect
 ap.add_argument("--stats", action="store_true")
 ap.add_argument("--no-detail", action="store_true")
+ap.add_argument("--world", type=int, default=1)     # render rank 0's share of an N-rank interleaved row partition
 a = ap.parse_args()
 cfg = scenes.CONFIGS[a.config]
 w, h, spp = a.w or cfg["w"], a.h or cfg["h"], a.spp or cfg["spp"]
@@ -33,9 +34,17 @@ if a.rows:
 r.set_detailed_timing(not a.no_detail)
 if a.stats:
     r.stats_enable(True)
+bands = None
+if a.world > 1:
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+    bands = bench.my_rows(h, 0, a.world)
 for i in range(a.passes):
     r.get_stats(reset=True)
-    r.render_pass(spp, rect=rect, frame_count=0)
+    if bands:
+        r.render_pass_bands(spp, bands, frame_count=0)
+    else:
+        r.render_pass(spp, rect=rect, frame_count=0)
     r.sync()
 t = r.pass_timing()
 st = r.get_stats().as_dict()
