@@ -13,8 +13,8 @@ pass (strong scaling).
 `value`     device-timed whole-job Mrays/s with the scene resident in HBM (CUDA events, max over ranks).
 `e2e`       the same metric through the public C-ABI with host buffers: every step re-uploads the host scene
             (bpt_upload_scene: flatten + H2D), renders, and downloads the film (D2H) inside the timed region.
-`roofline`  k_trace_closest: algorithmic bytes (reference binary-BVH visit counts x SURVEY 8d byte sizes) / its summed
-            launch time, against the measured HBM bandwidth.
+`roofline`  persistent_trace (all traversal launches): algorithmic bytes (reference binary-BVH visit counts x SURVEY 8d
+            byte sizes) / their summed launch time, against the measured HBM bandwidth.
 `cpu_baseline` / `--impl reference`: the reference's own tile-multithreaded CPU renderer (oracle/_ref, built from
             /root/reference unmodified) on this box's host cores, on a bounded sample of the same workload.
 """
@@ -311,24 +311,32 @@ def main():
             dist.destroy_process_group()
         return 0
 
-    # --- roofline of the dominant kernel (closest-hit traversal), this rank's launches ---
+    # --- roofline of the dominant kernel: persistent_trace (trace.cuh), launched as k_trace_closest (bounce 0),
+    #     k_trace_merged (extension rays of bounce b + shadow rays of bounce b-1) and k_trace_shadow (last bounce).
+    #     algorithmic bytes = reference binary-BVH visit counts of ALL rays x SURVEY 8d sizes; time = the summed
+    #     CUDA-event duration of all those launches in one pass (events on the launching stream).
     peak, peak_src = measured_peaks()
     bytes_closest = algorithmic_bytes(st_counts, shadow=False)
     bytes_shadow = algorithmic_bytes(st_counts, shadow=True)
     closest_rays = st_counts.rays - st_counts.shadow_rays
-    achieved = bytes_closest / (trace_ms * 1e-3) / 1e9 if trace_ms > 0 else None
-    roofline = {"bound": "hbm", "kernel": "k_trace_closest", "achieved": achieved, "peak": peak, "unit": "GB/s",
+    trav_ms = trace_ms + shadow_ms
+    achieved = (bytes_closest + bytes_shadow) / (trav_ms * 1e-3) / 1e9 if trav_ms > 0 else None
+    roofline = {"bound": "hbm", "kernel": "persistent_trace (k_trace_closest + k_trace_merged + k_trace_shadow launches)",
+                "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": (achieved / peak) if achieved else None, "traffic": None, "peak_source": peak_src,
-                "algorithmic_bytes_per_ray": bytes_closest / max(1, closest_rays),
-                "kernel_ms_per_step": trace_ms, "launches_per_step": trace_launches // 2,
-                "shadow_kernel": {"achieved": bytes_shadow / (shadow_ms * 1e-3) / 1e9 if shadow_ms > 0 else None,
-                                  "algorithmic_bytes_per_ray": bytes_shadow / max(1, st_counts.shadow_rays),
-                                  "kernel_ms_per_step": shadow_ms},
-                "stage_ms_per_step": {"raygen": raygen_ms, "trace_closest": trace_ms, "shade": shade_ms,
-                                      "trace_shadow": shadow_ms, "splat": splat_ms}}
-    traffic_file = os.path.join(ROOT, "profiles", "trace_closest_dram_bytes.json")
+                "algorithmic_bytes_per_ray": (bytes_closest + bytes_shadow) / max(1, st_counts.rays),
+                "algorithmic_bytes_per_launch": (bytes_closest + bytes_shadow) / max(1, trace_launches),
+                "closest_bytes_per_ray": bytes_closest / max(1, closest_rays),
+                "shadow_bytes_per_ray": bytes_shadow / max(1, st_counts.shadow_rays),
+                "kernel_ms_per_step": trav_ms, "launches_per_step": trace_launches,
+                "avg_launch_ms": trav_ms / max(1, trace_launches),
+                "stage_ms_per_step": {"raygen": raygen_ms, "trace_closest_and_merged": trace_ms, "shade": shade_ms,
+                                      "trace_shadow_last_bounce": shadow_ms, "splat": splat_ms}}
+    traffic_file = os.path.join(ROOT, "profiles", "trace_dram_bytes.json")
     if os.path.exists(traffic_file):
-        roofline["traffic"] = json.load(open(traffic_file)).get("dram_bytes_per_launch")
+        tf = json.load(open(traffic_file))
+        roofline["traffic"] = tf.get("dram_bytes_per_launch")
+        roofline["traffic_source"] = tf.get("source")
 
     rps = rays_all / samples_all
     os.makedirs(os.path.join(ROOT, "profiles"), exist_ok=True)

@@ -22,6 +22,7 @@ namespace {
 enum SceneSlot { SL_MATERIALS, SL_PRIMITIVES, SL_PLANES, SL_MESHES, SL_LIGHTS, SL_TLAS_NODES, SL_TLAS_INDICES, SL_BLAS_NODES,
                  SL_TRIANGLES, SL_TRI_ORIGINAL, SL_RAW_TRIANGLES, SL_NORMALS, SL_RAW_NORMALS, SL_SKYDOME, SL_RAW_SKYDOME };
 
+#define BPT_MAX_PIPES 4
 enum Stage { ST_RAYGEN, ST_TRACE, ST_SHADE, ST_SHADOW, ST_SPLAT, ST_COUNT };
 
 struct TimedSpan { cudaEvent_t a, b; int stage; };
@@ -62,8 +63,10 @@ struct bpt_ctx {
         std::vector<void*> allocs;
         bpt_sample_record* d_records = nullptr;
         uint64_t d_record_capacity = 0;
-    } pipes[2];
+    } pipes[BPT_MAX_PIPES];
     int n_pipes = 2;
+    uint32_t min_batches = 0;             // experiment knob (BPT_MIN_BATCHES): at least this many batches per pass
+    uint32_t tail_threshold = 32768;      // paths: at or below this many survivors a batch finishes inside k_tail (0 = never)
     bool merge_traces = true;             // trace bounce b's extension rays and bounce b-1's shadow rays in one launch
     int32_t* d_row_map = nullptr;
     uint32_t row_map_capacity = 0;
@@ -229,7 +232,9 @@ int bpt_create(int device, bpt_ctx** out_ctx) {
     }
     if (const char* e = getenv("BPT_REFILL")) { int v = atoi(e); if (v >= 1 && v <= 33) ctx->refill = (uint32_t)v; }
     if (const char* e = getenv("BPT_MERGE_TRACES")) ctx->merge_traces = atoi(e) != 0;
-    if (const char* e = getenv("BPT_PIPES")) { int v = atoi(e); if (v >= 1 && v <= 2) ctx->n_pipes = v; }
+    if (const char* e = getenv("BPT_TAIL_THRESHOLD")) { long v = atol(e); if (v >= 0 && v <= (1 << 22)) ctx->tail_threshold = (uint32_t)v; }
+    if (const char* e = getenv("BPT_PIPES")) { int v = atoi(e); if (v >= 1 && v <= BPT_MAX_PIPES) ctx->n_pipes = v; }
+    if (const char* e = getenv("BPT_MIN_BATCHES")) { int v = atoi(e); if (v >= 1 && v <= 64) ctx->min_batches = (uint32_t)v; }
     if (const char* e = getenv("BPT_TRACE_CTAS")) { int v = atoi(e); if (v >= 1 && v <= 32) ctx->trace_ctas_per_sm = v; }
     const char* dt = getenv("BPT_DETAILED_TIMING");
     ctx->detailed_timing = dt && atoi(dt) != 0;
@@ -579,16 +584,24 @@ retry_shape:
     S = (uint32_t)std::min<uint64_t>(spp, std::max<uint64_t>(1, cap / rect_w));
     rows_per_batch = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(rect_h, cap / ((uint64_t)rect_w*S)));
     n_batches = (uint64_t)((spp + S - 1)/S) * ((rect_h + rows_per_batch - 1)/rows_per_batch);
-    if (n_batches == 1 && n_pipes == 2 && S == spp && rect_h >= 2 && (uint64_t)rect_w*rect_h*spp >= (2ull << 20)) {
-        // a single batch cannot overlap with anything: split it so the two pipelines hide each other's kernel tails
-        rows_per_batch = (rect_h + 1)/2;
-        n_batches = 2;
+    {
+        // fewer batches than pipelines cannot overlap: split the rows so that every pipeline gets a batch and the
+        // pipelines hide each other's kernel tails (only worth it when each batch still fills the machine)
+        uint64_t row_batches = (rect_h + rows_per_batch - 1)/rows_per_batch;
+        uint64_t want = std::max<uint64_t>(ctx->min_batches, (uint64_t)n_pipes);
+        uint64_t total = (uint64_t)rect_w*rect_h*spp;
+        while (want > 1 && total/want < (1ull << 20) && want > ctx->min_batches) --want;
+        if (S == spp && row_batches < want && rect_h >= want) {
+            rows_per_batch = (uint32_t)((rect_h + want - 1)/want);
+            n_batches = (rect_h + rows_per_batch - 1)/rows_per_batch;
+        }
     }
-    if (n_batches < (uint64_t)n_pipes) n_pipes = 1;
-    if (n_pipes == 2 && ((rect_h + rows_per_batch - 1)/rows_per_batch) & 1) {
-        // even out the last pair of batches
-        uint32_t nb = (rect_h + rows_per_batch - 1)/rows_per_batch + 1;
-        rows_per_batch = (rect_h + nb - 1)/nb;
+    if (n_batches < (uint64_t)n_pipes) n_pipes = (int)n_batches;
+    if (n_pipes >= 2) {
+        // even out the batches of the last round over the pipelines
+        uint32_t nb = (rect_h + rows_per_batch - 1)/rows_per_batch;
+        uint32_t rounded = ((nb + n_pipes - 1)/n_pipes)*n_pipes;
+        if (rounded != nb && rect_h >= rounded) rows_per_batch = (rect_h + rounded - 1)/rounded;
     }
     uint64_t slots64 = (uint64_t)rect_w*rows_per_batch*S;
     if (slots64 > 0x7FFFFFFFull) { set_error("%s: batch too large", who); return BPT_ERR_ARG; }
@@ -624,7 +637,7 @@ retry_shape:
         ctx->row_map_capacity = std::max<uint32_t>(rect_h, 4096);
     }
     // the previous pass may still be reading the old row map on the pipe streams: order the copy after them
-    for (int p = 0; p < 2; ++p) { CK(cudaEventRecord(ctx->pipes[p].done, ctx->pipes[p].stream)); CK(cudaStreamWaitEvent(ctx->stream, ctx->pipes[p].done, 0)); }
+    for (int p = 0; p < BPT_MAX_PIPES; ++p) { CK(cudaEventRecord(ctx->pipes[p].done, ctx->pipes[p].stream)); CK(cudaStreamWaitEvent(ctx->stream, ctx->pipes[p].done, 0)); }
     CK(cudaMemcpyAsync(ctx->d_row_map, rows.data(), (size_t)rect_h*sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
 
     ctx->spans_used = 0;
@@ -657,8 +670,8 @@ retry_shape:
             // Per bounce b:  trace { extension rays of b  +  shadow rays queued by bounce b-1 }  ->  shade b.
             // counters: [0]/[1] = active-queue sizes (ping-pong), [2] = shadow count, [3] = fetch cursor.
             // With the counting instantiations (stats) the two populations are traced by separate launches.
-            // (also when per-kernel timing is requested, so that each kernel's own duration is what gets measured)
-            const bool merged = !stats && !ctx->detailed_timing && ctx->merge_traces;
+            // Per-kernel timing: ST_TRACE spans k_trace_closest (bounce 0) + k_trace_merged, ST_SHADOW the final k_trace_shadow.
+            const bool merged = !stats && ctx->merge_traces;
             for (uint32_t bounce = 0; bounce < max_bounce; ++bounce) {
                 int in = bounce & 1, out = in ^ 1;
                 const uint32_t* in_queue = bounce == 0 ? nullptr : pp.q.active[in];
@@ -681,6 +694,14 @@ retry_shape:
                 // the shadow items of the previous bounce are consumed (merged) or not yet produced: reset before shading
                 k_reset_counters<<<1, 32, 0, s>>>(counters, (1 << out) | (1 << 2));
                 ctx->launches++;
+                if (merged && bounce > 0 && ctx->tail_threshold > 0) {
+                    // few survivors: finish them inside one launch; the wavefront launches below then find empty queues
+                    k_tail_decide<<<1, 32, 0, s>>>(counters, in, ctx->tail_threshold);
+                    begin_span(ctx, ST_TRACE, s);
+                    k_tail<<<(ctx->tail_threshold + 127)/128, 128, 0, s>>>(sc, pp.st, b, bounce, pp.q.active[in], counters + 8, ctx->d_stats);
+                    end_span(ctx, s);
+                    ctx->launches += 2; ctx->trace_launches++;
+                }
                 begin_span(ctx, ST_SHADE, s);
                 k_shade<<<grid_for(ctx, work, 128, 16), 128, 0, s>>>(sc, pp.st, b, bounce, in_queue, in_count, b.slots,
                                                                     pp.q.active[out], counters + out, pp.q.shadow, counters + 2, ctx->d_stats);
@@ -762,9 +783,12 @@ int bpt_get_pass_timing(bpt_ctx* ctx, bpt_pass_timing* out) {
     CK(cudaEventSynchronize(ctx->pass_end));
     CK(cudaEventElapsedTime(&out->total_ms, ctx->pass_begin, ctx->pass_end));
     float acc[ST_COUNT] = {0, 0, 0, 0, 0};
+    const bool dump = getenv("BPT_DUMP_SPANS") != nullptr;
+    static const char* stage_names[ST_COUNT] = {"raygen", "trace", "shade", "shadow", "splat"};
     for (size_t i = 0; i < ctx->spans_used; ++i) {
         float ms = 0.0f;
         if (cudaEventElapsedTime(&ms, ctx->spans[i].a, ctx->spans[i].b) == cudaSuccess) acc[ctx->spans[i].stage] += ms;
+        if (dump) fprintf(stderr, "span %3zu %-7s %9.4f ms\n", i, stage_names[ctx->spans[i].stage], ms);
     }
     out->raygen_ms = acc[ST_RAYGEN]; out->trace_ms = acc[ST_TRACE]; out->shade_ms = acc[ST_SHADE];
     out->shadow_ms = acc[ST_SHADOW]; out->splat_ms = acc[ST_SPLAT];
@@ -797,6 +821,13 @@ int bpt_resolve_bgra8(bpt_ctx* ctx, const bpt_post_settings* post, const uint8_t
     cudaFree(d_out); cudaFree(d_dither);
     if (e != cudaSuccess) { set_error("bpt_resolve_bgra8: %s", cudaGetErrorString(e)); return BPT_ERR_CUDA; }
     ctx->d2h_bytes += n*sizeof(uint32_t);
+    return BPT_OK;
+}
+
+int bpt_set_tail_threshold(bpt_ctx* ctx, uint32_t paths) {
+    if (!ctx) { set_error("bpt_set_tail_threshold: null ctx"); return BPT_ERR_ARG; }
+    if (paths > (1u << 22)) { set_error("bpt_set_tail_threshold: at most %u paths", 1u << 22); return BPT_ERR_ARG; }
+    ctx->tail_threshold = paths;
     return BPT_OK;
 }
 

@@ -290,7 +290,7 @@ BPT_D void flush_ray_counts(DStats* stats, uint32_t rays, uint32_t shadow) {
 }
 
 #ifndef BPT_TRACE_MIN_CTAS
-#define BPT_TRACE_MIN_CTAS 7
+#define BPT_TRACE_MIN_CTAS 8      // 64 registers: +3.4 % on C2 over 7 CTAs/72 registers (latency-bound: more resident warps win); 9 and 10 CTAs lose to spills
 #endif
 
 struct ClosestSrc {        // rays come from the path state (through the active queue), hits go back to it
@@ -355,7 +355,7 @@ k_trace_merged(DScene sc, DPathState st, const uint32_t* __restrict__ in_queue, 
     uint32_t nc = *n_closest_ptr, ns = *n_shadow_ptr;
     TraceCounters ctr = {};
     MergedSrc src = {{st, in_queue, sc.normals != nullptr}, {st, items}, nc};
-    persistent_trace<TRACE_MODE_MIXED, false>(sc, src, nc + ns, cursor, refill, ctr);
+    persistent_trace<TRACE_MODE_MIXED, false, false>(sc, src, nc + ns, cursor, refill, ctr);
 }
 
 // intersect_scene for every active path (integrators.cpp:615).  in_queue == nullptr means "slot = i".
@@ -366,7 +366,7 @@ k_trace_closest(DScene sc, DPathState st, const uint32_t* __restrict__ in_queue,
     uint32_t n = n_ptr ? *n_ptr : n_fixed;
     TraceCounters ctr = {};
     ClosestSrc src = {st, in_queue, sc.normals != nullptr};
-    persistent_trace<TRACE_MODE_CLOSEST, STATS>(sc, src, n, cursor, refill, ctr);
+    persistent_trace<TRACE_MODE_CLOSEST, STATS, false>(sc, src, n, cursor, refill, ctr);
     if (STATS) flush_counters(stats, ctr, false);
 }
 
@@ -378,7 +378,7 @@ k_trace_shadow(DScene sc, DPathState st, const DShadowItem* __restrict__ items, 
     uint32_t n = *n_ptr;
     TraceCounters ctr = {};
     ShadowSrc src = {st, items};
-    persistent_trace<TRACE_MODE_OCCLUSION, STATS>(sc, src, n, cursor, refill, ctr);
+    persistent_trace<TRACE_MODE_OCCLUSION, STATS, false>(sc, src, n, cursor, refill, ctr);
     if (STATS) flush_counters(stats, ctr, true);
 }
 
@@ -394,7 +394,236 @@ BPT_D uint32_t queue_append(uint32_t* counter, bool want) {
     return base + __popc(mask & ((1u << lane) - 1u));
 }
 
-// One bounce of advanced_integrator (integrators.cpp:612-818) for every active path.
+// One bounce of advanced_integrator (integrators.cpp:612-818) for ONE path: reads the path's state and the hit of its
+// current ray, accumulates emission / sky, draws the next direction, and reports whether the path continues
+// (its next ray is then in st.ray_o/ray_d) and whether it queued an NEE shadow ray (`sh`).
+BPT_D void shade_path(const DScene& sc, const DPathState& st, const BatchDesc& b, uint32_t bounce, uint32_t slot,
+                      bool& alive, bool& want_shadow, DShadowItem& sh) {
+    const bpt_settings& set = sc.settings;
+    float4 ro4 = st.ray_o[slot], rd4 = st.ray_d[slot], h4 = st.hit[slot];
+    V3 ro = v3(ro4), rd = v3(rd4);
+    HitRecord h;
+    h.t = h4.x; h.prim = __float_as_uint(h4.y); h.tri = __float_as_uint(h4.z); h.v = h4.w; h.w = sc.normals ? st.hit_w[slot] : 0.0f;
+    float4 tp4 = st.throughput[slot];
+    V3 throughput = v3(tp4);
+    float4 rad4 = st.radiance[slot];
+    V3 total = v3(rad4);
+    float4 pd = make_float4(0, 0, 0, 0);
+    if (b.want_records) pd = st.primary_d[slot];
+    uint32_t ray_count = __float_as_uint(pd.w) + 1u;      // this bounce's intersect_scene call
+    bool total_changed = false;
+
+    if (h.prim == BPT_HIT_MISS) {
+        total = total + throughput*sample_sky(sc, rd);                                     // :813
+        total_changed = true;
+    } else {
+        SamplerCtx sm = make_sampler(sc, b, slot);
+        uint4 rng = st.rng[slot];
+        float4 pn4 = st.prev_n[slot];
+        V3 prev_N = v3(pn4);
+        bool is_specular = (__float_as_uint(pn4.w) & 1u) != 0;
+        int stack_at = st.mstack_at[slot];
+
+        V3 I, N;
+        uint32_t surface_id;
+        hit_geometry(sc, ro, rd, h, I, N, surface_id);
+        float t = h.t;
+
+        float cos_i = -dot(rd, N);                                                          // :618
+        bool inside = (cos_i < 0.0f);
+        uint32_t id_i, id_t;
+        if (inside) {
+            id_i = surface_id;
+            int below = stack_at - 1; if (below < 0) below = 0;
+            id_t = st.mstack[(size_t)below*b.slots + slot];
+            cos_i = -cos_i;
+            N = -N;
+        } else {
+            id_i = st.mstack[(size_t)stack_at*b.slots + slot];
+            id_t = surface_id;
+        }
+        MatView mi = load_material(sc, id_i);
+        MatView mt = load_material(sc, id_t);
+
+        if (mi.medium) {                                                                     // :640-649 Beer
+            V3 absorption = v3(exp_f(-mi.absorb.x*t), exp_f(-mi.absorb.y*t), exp_f(-mi.absorb.z*t));
+            throughput = throughput*absorption;
+        }
+
+        if (mt.flags & BPT_MATERIAL_EMISSIVE) {                                              // :651-670
+            bool allow_direct = (!set.next_event_estimation ||
+                                 ((set.caustics || (bounce < 2)) && is_specular));
+            if (allow_direct) {
+                total = total + throughput*mt.emission;
+                total_changed = true;
+            } else if (bounce > 0 && set.use_mis) {
+                float light_distance_sq = t*t;
+                float light_pdf = light_distance_sq / cos_i;
+                float brdf_pdf = (set.importance_sample_diffuse ? dot(prev_N, rd) / kPi : 1.0f / (2.0f*kPi));
+                float mis_pdf = light_pdf + brdf_pdf;
+                total = total + (1.0f / mis_pdf)*throughput*mt.emission;
+                total_changed = true;
+            }
+        } else {
+            alive = true;
+            float eta_i = mi.ior, eta_t = mt.ior;
+            float ratio = eta_i / eta_t;
+            float cos_t;
+            float reflectance = fresnel_dielectric(cos_i, eta_i, eta_t, ratio, cos_t);
+            float reflect_test = sample_1d(sm, rng, Sample_Reflectance, bounce);
+            reflectance = lerp_f(reflectance, 1.0f, mt.metallic);
+            is_specular = true;
+            V3 next_o, next_d;
+
+            if (reflect_test < reflectance) {                                                // :684-696
+                V3 refl = reflect(rd, N);
+                if (mt.roughness > 0.0f) {
+                    V3 rs;
+                    do {                                                                     // random_in_unit_sphere :11-19
+                        next_set(rng);
+                        rs = v3(bilateral(rng.x), bilateral(rng.y), bilateral(rng.z));
+                    } while (length_sq(rs) >= 1.0f);
+                    refl = normalize((1.0f + kEps)*refl + mt.roughness*rs);
+                }
+                next_o = I + kEps*refl; next_d = refl;
+                throughput = throughput*lerp_v(v3(1.0f), mt.albedo, mt.metallic);
+            } else if (mt.medium) {                                                          // :698-717 refract
+                if (inside) {
+                    if (stack_at > 0) --stack_at;
+                } else if (stack_at < (BPT_MATERIAL_STACK_DEPTH - 1)) {
+                    ++stack_at;
+                    st.mstack[(size_t)stack_at*b.slots + slot] = (uint16_t)id_t;
+                }
+                V3 refr = ratio*rd + N*(ratio*cos_i - cos_t);
+                next_o = I + refr*kEps; next_d = refr;
+            } else {                                                                         // :719-790 diffuse
+                is_specular = false;
+                V3 albedo = mt.albedo;
+                if (mt.flags & BPT_MATERIAL_CHECKERS) {
+                    int checker = (((int)floorf(0.25f*I.x)) ^ ((int)floorf(0.25f*I.z))) & 1;
+                    if (checker) albedo = mt.checker;
+                }
+                V3 brdf = (1.0f / kPi)*albedo;
+
+                if (set.next_event_estimation && (sc.light_count > 0)) {
+                    float pick = sample_1d(sm, rng, Sample_LightSelection, bounce);
+                    // pick_random_light (:135-192)
+                    uint32_t light_id = 0;
+                    float pick_pdf = 0.0f;
+                    if (set.importance_sample_lights) {
+                        float sum = 0.0f;
+                        for (uint32_t li = 0; li < sc.light_count; ++li) {
+                            const DPrimitive* lp = sc.primitives + __ldg(&sc.lights[li]);
+                            V3 lv = v3(__ldg(&lp->fwd[0].w), __ldg(&lp->fwd[1].w), __ldg(&lp->fwd[2].w)) - I;
+                            float dsq = length_sq(lv);
+                            const DMaterial* lm = sc.materials + __ldg(&lp->material);
+                            float l = max3(v3(__ldg(&lm->emission_color[0]), __ldg(&lm->emission_color[1]), __ldg(&lm->emission_color[2])));
+                            float r = __ldg(&lp->sphere_r);
+                            float psa = (__ldg(&lp->type) == BPT_PRIM_SPHERE) ? (kPi*r*r / dsq) : 0.0f;
+                            sum += l*psa;
+                        }
+                        float e = sum*pick;
+                        float cdf = 0.0f, pdf = 0.0f;
+                        uint32_t li = 0;
+                        for (;; ++li) {
+                            const DPrimitive* lp = sc.primitives + __ldg(&sc.lights[li]);
+                            V3 lv = v3(__ldg(&lp->fwd[0].w), __ldg(&lp->fwd[1].w), __ldg(&lp->fwd[2].w)) - I;
+                            float dsq = length_sq(lv);
+                            const DMaterial* lm = sc.materials + __ldg(&lp->material);
+                            float l = max3(v3(__ldg(&lm->emission_color[0]), __ldg(&lm->emission_color[1]), __ldg(&lm->emission_color[2])));
+                            float r = __ldg(&lp->sphere_r);
+                            float psa = (__ldg(&lp->type) == BPT_PRIM_SPHERE) ? (kPi*r*r / dsq) : 0.0f;
+                            pdf = l*psa;
+                            cdf = cdf + pdf;
+                            if (!(cdf < e) || li + 1 >= sc.light_count) break;
+                        }
+                        pick_pdf = pdf / sum;
+                        light_id = __ldg(&sc.lights[li]);
+                    } else {
+                        pick_pdf = 1.0f / (float)sc.light_count;
+                        uint32_t li = (uint32_t)(pick*(float)sc.light_count - kEps);
+                        light_id = __ldg(&sc.lights[li]);
+                    }
+
+                    V2 ds = sample_2d(sm, rng, Sample_DirectLighting, bounce);
+                    const DPrimitive* lp = sc.primitives + light_id;
+                    if (__ldg(&lp->type) == BPT_PRIM_SPHERE) {
+                        // random_point_on_light (:199-228)
+                        float4 f[3] = {__ldg(&lp->fwd[0]), __ldg(&lp->fwd[1]), __ldg(&lp->fwd[2])};
+                        float lr = __ldg(&lp->sphere_r);
+                        V3 light_p = v3(f[0].w, f[1].w, f[2].w);
+                        V3 towards = normalize(light_p - I);
+                        V3 Nl = map_to_hemisphere(-towards, ds);
+                        V3 p = Nl*lr;
+                        V3 p_world = xform(f, p, 1.0f);
+                        V3 L = p_world - I;
+                        float dist_sq = length_sq(L);
+                        float dist = sqrtf(dist_sq);
+                        L = L / dist;
+                        float A = 2.0f*kPi*lr*lr;
+
+                        float N_dot_L = dot(N, L);
+                        float neg_Nl_dot_L = -dot(Nl, L);
+                        if (N_dot_L > 0.0f && neg_Nl_dot_L > 0.0f) {
+                            float solid_angle = (neg_Nl_dot_L*A) / dist_sq;
+                            float pdf;
+                            if (set.use_mis) {
+                                float light_pdf = 1.0f / solid_angle;
+                                float brdf_pdf = (set.importance_sample_diffuse ? N_dot_L / kPi : 1.0f / (2.0f*kPi));
+                                pdf = light_pdf + brdf_pdf;
+                            } else {
+                                pdf = 1.0f / solid_angle;
+                            }
+                            pdf *= pick_pdf;
+                            const DMaterial* lm = sc.materials + __ldg(&lp->material);
+                            V3 emission = v3(__ldg(&lm->emission_color[0]), __ldg(&lm->emission_color[1]), __ldg(&lm->emission_color[2]));
+                            V3 contrib = throughput*(dot(N, L) / pdf)*brdf*emission;
+                            V3 so = I + L*kEps;
+                            sh.o_maxt = make_float4(so.x, so.y, so.z, dist - 2*kEps);
+                            sh.d_light = make_float4(L.x, L.y, L.z, __uint_as_float(light_id));
+                            sh.contrib_slot = make_float4(contrib.x, contrib.y, contrib.z, __uint_as_float(slot));
+                            want_shadow = true;
+                            ray_count += 1u;
+                        }
+                    }
+                }
+
+                V2 is = sample_2d(sm, rng, Sample_IndirectLighting, bounce);
+                V3 R;
+                if (set.importance_sample_diffuse) {
+                    R = map_to_cosine_weighted_hemisphere(N, is);
+                    throughput = throughput*kPi;
+                } else {
+                    R = map_to_hemisphere(N, is);
+                    throughput = throughput*(2.0f*kPi*dot(N, R));
+                }
+                throughput = throughput*brdf;
+                next_o = I + N*kEps; next_d = R;
+            }
+
+            if (set.russian_roulette && !is_specular) {                                      // :801-811
+                float p = clamp_t(max3(throughput), 0.1f, 0.9f);
+                float e = sample_1d(sm, rng, Sample_Roulette, bounce);
+                if (e > p) alive = false;
+                else throughput = throughput*(1.0f / p);
+            }
+
+            if (bounce + 1 >= set.max_bounce_count) alive = false;
+            if (alive) {
+                st.ray_o[slot] = make_float4(next_o.x, next_o.y, next_o.z, 3.402823466e+38f);
+                st.ray_d[slot] = make_float4(next_d.x, next_d.y, next_d.z, 0.0f);
+                st.rng[slot] = rng;
+                st.prev_n[slot] = make_float4(N.x, N.y, N.z, __uint_as_float(is_specular ? 1u : 0u));
+                st.mstack_at[slot] = (uint8_t)stack_at;
+                st.throughput[slot] = make_float4(throughput.x, throughput.y, throughput.z, tp4.w);
+            }
+        }
+    }
+    if (total_changed) st.radiance[slot] = make_float4(total.x, total.y, total.z, 0.0f);
+    if (b.want_records) { pd.w = __uint_as_float(ray_count); st.primary_d[slot] = pd; }
+}
+
+// One bounce for every active path of the batch (wavefront form of the loop at integrators.cpp:612-818).
 #ifndef BPT_SHADE_MIN_CTAS
 #define BPT_SHADE_MIN_CTAS 8      // 64 registers: measured 14.7 ms vs 18.6 ms at 4 CTAs/128 registers on C2 (latency-bound on path state)
 #endif
@@ -407,7 +636,6 @@ k_shade(DScene sc, DPathState st, BatchDesc b, uint32_t bounce,
     uint32_t n_rays = 0, n_shadow = 0;
     uint32_t stride = gridDim.x*blockDim.x;
     uint32_t base = blockIdx.x*blockDim.x + threadIdx.x;
-    const bpt_settings& set = sc.settings;
 
     for (uint32_t i0 = base - (threadIdx.x & 31); i0 < n; i0 += stride) {
         uint32_t i = i0 + (threadIdx.x & 31);
@@ -418,227 +646,7 @@ k_shade(DScene sc, DPathState st, BatchDesc b, uint32_t bounce,
 
         if (i < n) {
             slot = in_queue ? in_queue[i] : i;
-            float4 ro4 = st.ray_o[slot], rd4 = st.ray_d[slot], h4 = st.hit[slot];
-            V3 ro = v3(ro4), rd = v3(rd4);
-            HitRecord h;
-            h.t = h4.x; h.prim = __float_as_uint(h4.y); h.tri = __float_as_uint(h4.z); h.v = h4.w; h.w = sc.normals ? st.hit_w[slot] : 0.0f;
-            float4 tp4 = st.throughput[slot];
-            V3 throughput = v3(tp4);
-            float4 rad4 = st.radiance[slot];
-            V3 total = v3(rad4);
-            float4 pd = make_float4(0, 0, 0, 0);
-            if (b.want_records) pd = st.primary_d[slot];
-            uint32_t ray_count = __float_as_uint(pd.w) + 1u;      // this bounce's intersect_scene call
-            bool total_changed = false;
-
-            if (h.prim == BPT_HIT_MISS) {
-                total = total + throughput*sample_sky(sc, rd);                                     // :813
-                total_changed = true;
-            } else {
-                SamplerCtx sm = make_sampler(sc, b, slot);
-                uint4 rng = st.rng[slot];
-                float4 pn4 = st.prev_n[slot];
-                V3 prev_N = v3(pn4);
-                bool is_specular = (__float_as_uint(pn4.w) & 1u) != 0;
-                int stack_at = st.mstack_at[slot];
-
-                V3 I, N;
-                uint32_t surface_id;
-                hit_geometry(sc, ro, rd, h, I, N, surface_id);
-                float t = h.t;
-
-                float cos_i = -dot(rd, N);                                                          // :618
-                bool inside = (cos_i < 0.0f);
-                uint32_t id_i, id_t;
-                if (inside) {
-                    id_i = surface_id;
-                    int below = stack_at - 1; if (below < 0) below = 0;
-                    id_t = st.mstack[(size_t)below*b.slots + slot];
-                    cos_i = -cos_i;
-                    N = -N;
-                } else {
-                    id_i = st.mstack[(size_t)stack_at*b.slots + slot];
-                    id_t = surface_id;
-                }
-                MatView mi = load_material(sc, id_i);
-                MatView mt = load_material(sc, id_t);
-
-                if (mi.medium) {                                                                     // :640-649 Beer
-                    V3 absorption = v3(exp_f(-mi.absorb.x*t), exp_f(-mi.absorb.y*t), exp_f(-mi.absorb.z*t));
-                    throughput = throughput*absorption;
-                }
-
-                if (mt.flags & BPT_MATERIAL_EMISSIVE) {                                              // :651-670
-                    bool allow_direct = (!set.next_event_estimation ||
-                                         ((set.caustics || (bounce < 2)) && is_specular));
-                    if (allow_direct) {
-                        total = total + throughput*mt.emission;
-                        total_changed = true;
-                    } else if (bounce > 0 && set.use_mis) {
-                        float light_distance_sq = t*t;
-                        float light_pdf = light_distance_sq / cos_i;
-                        float brdf_pdf = (set.importance_sample_diffuse ? dot(prev_N, rd) / kPi : 1.0f / (2.0f*kPi));
-                        float mis_pdf = light_pdf + brdf_pdf;
-                        total = total + (1.0f / mis_pdf)*throughput*mt.emission;
-                        total_changed = true;
-                    }
-                } else {
-                    alive = true;
-                    float eta_i = mi.ior, eta_t = mt.ior;
-                    float ratio = eta_i / eta_t;
-                    float cos_t;
-                    float reflectance = fresnel_dielectric(cos_i, eta_i, eta_t, ratio, cos_t);
-                    float reflect_test = sample_1d(sm, rng, Sample_Reflectance, bounce);
-                    reflectance = lerp_f(reflectance, 1.0f, mt.metallic);
-                    is_specular = true;
-                    V3 next_o, next_d;
-
-                    if (reflect_test < reflectance) {                                                // :684-696
-                        V3 refl = reflect(rd, N);
-                        if (mt.roughness > 0.0f) {
-                            V3 rs;
-                            do {                                                                     // random_in_unit_sphere :11-19
-                                next_set(rng);
-                                rs = v3(bilateral(rng.x), bilateral(rng.y), bilateral(rng.z));
-                            } while (length_sq(rs) >= 1.0f);
-                            refl = normalize((1.0f + kEps)*refl + mt.roughness*rs);
-                        }
-                        next_o = I + kEps*refl; next_d = refl;
-                        throughput = throughput*lerp_v(v3(1.0f), mt.albedo, mt.metallic);
-                    } else if (mt.medium) {                                                          // :698-717 refract
-                        if (inside) {
-                            if (stack_at > 0) --stack_at;
-                        } else if (stack_at < (BPT_MATERIAL_STACK_DEPTH - 1)) {
-                            ++stack_at;
-                            st.mstack[(size_t)stack_at*b.slots + slot] = (uint16_t)id_t;
-                        }
-                        V3 refr = ratio*rd + N*(ratio*cos_i - cos_t);
-                        next_o = I + refr*kEps; next_d = refr;
-                    } else {                                                                         // :719-790 diffuse
-                        is_specular = false;
-                        V3 albedo = mt.albedo;
-                        if (mt.flags & BPT_MATERIAL_CHECKERS) {
-                            int checker = (((int)floorf(0.25f*I.x)) ^ ((int)floorf(0.25f*I.z))) & 1;
-                            if (checker) albedo = mt.checker;
-                        }
-                        V3 brdf = (1.0f / kPi)*albedo;
-
-                        if (set.next_event_estimation && (sc.light_count > 0)) {
-                            float pick = sample_1d(sm, rng, Sample_LightSelection, bounce);
-                            // pick_random_light (:135-192)
-                            uint32_t light_id = 0;
-                            float pick_pdf = 0.0f;
-                            if (set.importance_sample_lights) {
-                                float sum = 0.0f;
-                                for (uint32_t li = 0; li < sc.light_count; ++li) {
-                                    const DPrimitive* lp = sc.primitives + __ldg(&sc.lights[li]);
-                                    V3 lv = v3(__ldg(&lp->fwd[0].w), __ldg(&lp->fwd[1].w), __ldg(&lp->fwd[2].w)) - I;
-                                    float dsq = length_sq(lv);
-                                    const DMaterial* lm = sc.materials + __ldg(&lp->material);
-                                    float l = max3(v3(__ldg(&lm->emission_color[0]), __ldg(&lm->emission_color[1]), __ldg(&lm->emission_color[2])));
-                                    float r = __ldg(&lp->sphere_r);
-                                    float psa = (__ldg(&lp->type) == BPT_PRIM_SPHERE) ? (kPi*r*r / dsq) : 0.0f;
-                                    sum += l*psa;
-                                }
-                                float e = sum*pick;
-                                float cdf = 0.0f, pdf = 0.0f;
-                                uint32_t li = 0;
-                                for (;; ++li) {
-                                    const DPrimitive* lp = sc.primitives + __ldg(&sc.lights[li]);
-                                    V3 lv = v3(__ldg(&lp->fwd[0].w), __ldg(&lp->fwd[1].w), __ldg(&lp->fwd[2].w)) - I;
-                                    float dsq = length_sq(lv);
-                                    const DMaterial* lm = sc.materials + __ldg(&lp->material);
-                                    float l = max3(v3(__ldg(&lm->emission_color[0]), __ldg(&lm->emission_color[1]), __ldg(&lm->emission_color[2])));
-                                    float r = __ldg(&lp->sphere_r);
-                                    float psa = (__ldg(&lp->type) == BPT_PRIM_SPHERE) ? (kPi*r*r / dsq) : 0.0f;
-                                    pdf = l*psa;
-                                    cdf = cdf + pdf;
-                                    if (!(cdf < e) || li + 1 >= sc.light_count) break;
-                                }
-                                pick_pdf = pdf / sum;
-                                light_id = __ldg(&sc.lights[li]);
-                            } else {
-                                pick_pdf = 1.0f / (float)sc.light_count;
-                                uint32_t li = (uint32_t)(pick*(float)sc.light_count - kEps);
-                                light_id = __ldg(&sc.lights[li]);
-                            }
-
-                            V2 ds = sample_2d(sm, rng, Sample_DirectLighting, bounce);
-                            const DPrimitive* lp = sc.primitives + light_id;
-                            if (__ldg(&lp->type) == BPT_PRIM_SPHERE) {
-                                // random_point_on_light (:199-228)
-                                float4 f[3] = {__ldg(&lp->fwd[0]), __ldg(&lp->fwd[1]), __ldg(&lp->fwd[2])};
-                                float lr = __ldg(&lp->sphere_r);
-                                V3 light_p = v3(f[0].w, f[1].w, f[2].w);
-                                V3 towards = normalize(light_p - I);
-                                V3 Nl = map_to_hemisphere(-towards, ds);
-                                V3 p = Nl*lr;
-                                V3 p_world = xform(f, p, 1.0f);
-                                V3 L = p_world - I;
-                                float dist_sq = length_sq(L);
-                                float dist = sqrtf(dist_sq);
-                                L = L / dist;
-                                float A = 2.0f*kPi*lr*lr;
-
-                                float N_dot_L = dot(N, L);
-                                float neg_Nl_dot_L = -dot(Nl, L);
-                                if (N_dot_L > 0.0f && neg_Nl_dot_L > 0.0f) {
-                                    float solid_angle = (neg_Nl_dot_L*A) / dist_sq;
-                                    float pdf;
-                                    if (set.use_mis) {
-                                        float light_pdf = 1.0f / solid_angle;
-                                        float brdf_pdf = (set.importance_sample_diffuse ? N_dot_L / kPi : 1.0f / (2.0f*kPi));
-                                        pdf = light_pdf + brdf_pdf;
-                                    } else {
-                                        pdf = 1.0f / solid_angle;
-                                    }
-                                    pdf *= pick_pdf;
-                                    const DMaterial* lm = sc.materials + __ldg(&lp->material);
-                                    V3 emission = v3(__ldg(&lm->emission_color[0]), __ldg(&lm->emission_color[1]), __ldg(&lm->emission_color[2]));
-                                    V3 contrib = throughput*(dot(N, L) / pdf)*brdf*emission;
-                                    V3 so = I + L*kEps;
-                                    sh.o_maxt = make_float4(so.x, so.y, so.z, dist - 2*kEps);
-                                    sh.d_light = make_float4(L.x, L.y, L.z, __uint_as_float(light_id));
-                                    sh.contrib_slot = make_float4(contrib.x, contrib.y, contrib.z, __uint_as_float(slot));
-                                    want_shadow = true;
-                                    ray_count += 1u;
-                                }
-                            }
-                        }
-
-                        V2 is = sample_2d(sm, rng, Sample_IndirectLighting, bounce);
-                        V3 R;
-                        if (set.importance_sample_diffuse) {
-                            R = map_to_cosine_weighted_hemisphere(N, is);
-                            throughput = throughput*kPi;
-                        } else {
-                            R = map_to_hemisphere(N, is);
-                            throughput = throughput*(2.0f*kPi*dot(N, R));
-                        }
-                        throughput = throughput*brdf;
-                        next_o = I + N*kEps; next_d = R;
-                    }
-
-                    if (set.russian_roulette && !is_specular) {                                      // :801-811
-                        float p = clamp_t(max3(throughput), 0.1f, 0.9f);
-                        float e = sample_1d(sm, rng, Sample_Roulette, bounce);
-                        if (e > p) alive = false;
-                        else throughput = throughput*(1.0f / p);
-                    }
-
-                    if (bounce + 1 >= set.max_bounce_count) alive = false;
-                    if (alive) {
-                        st.ray_o[slot] = make_float4(next_o.x, next_o.y, next_o.z, 3.402823466e+38f);
-                        st.ray_d[slot] = make_float4(next_d.x, next_d.y, next_d.z, 0.0f);
-                        st.rng[slot] = rng;
-                        st.prev_n[slot] = make_float4(N.x, N.y, N.z, __uint_as_float(is_specular ? 1u : 0u));
-                        st.mstack_at[slot] = (uint8_t)stack_at;
-                        st.throughput[slot] = make_float4(throughput.x, throughput.y, throughput.z, tp4.w);
-                    }
-                }
-            }
-            if (total_changed) st.radiance[slot] = make_float4(total.x, total.y, total.z, 0.0f);
-            if (b.want_records) { pd.w = __uint_as_float(ray_count); st.primary_d[slot] = pd; }
+            shade_path(sc, st, b, bounce, slot, alive, want_shadow, sh);
         }
 
         uint32_t qi = queue_append(out_count, alive);
@@ -647,6 +655,87 @@ k_shade(DScene sc, DPathState st, BatchDesc b, uint32_t bounce,
         if (want_shadow) shadow_items[si] = sh;
         n_rays += (i < n ? 1u : 0u) + (want_shadow ? 1u : 0u);
         n_shadow += want_shadow ? 1u : 0u;
+    }
+    flush_ray_counts(stats, n_rays, n_shadow);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Fused tail.  Once only a few paths of a batch are still alive, a wavefront bounce costs the latency of its longest
+// ray four launches over (the machine is empty), bounce after bounce.  k_tail_decide (one thread, between the trace
+// and the shade of a bounce) hands the survivors over when they fit: it moves the active count to tail[0] and zeroes
+// it, so the remaining wavefront launches of the batch find empty queues.  k_tail then carries each surviving path to
+// its end inside ONE launch: lane = path; per bounce shade_path (the same function k_shade runs), then the lane's
+// own shadow ray and extension ray through persistent_trace in LOCAL mode.  Per path the sequence of operations --
+// and of float additions into its radiance -- is the one the wavefront would have executed.
+struct TailSrc {
+    DPathState st;
+    DShadowItem sh;
+    uint32_t slot;
+    bool has_shadow, has_closest, cur_shadow, store_w;
+    BPT_D bool pending() const { return has_shadow || has_closest; }
+    BPT_D void next(V3& o, V3& d, float& max_t, uint32_t& ignored, bool& occ) {
+        if (has_shadow) {
+            o = v3(sh.o_maxt); d = v3(sh.d_light); max_t = sh.o_maxt.w; ignored = __float_as_uint(sh.d_light.w);
+            occ = true; has_shadow = false; cur_shadow = true;
+        } else {
+            float4 ro = st.ray_o[slot], rd = st.ray_d[slot];
+            o = v3(ro); d = v3(rd); max_t = ro.w; ignored = 0u;
+            occ = false; has_closest = false; cur_shadow = false;
+        }
+    }
+    BPT_D void store(uint32_t, const HitRecord& h) const {
+        if (cur_shadow) {
+            if (h.prim == BPT_HIT_MISS) {
+                float4 r = st.radiance[slot];
+                r.x = r.x + sh.contrib_slot.x; r.y = r.y + sh.contrib_slot.y; r.z = r.z + sh.contrib_slot.z;
+                st.radiance[slot] = r;
+            }
+        } else {
+            st.hit[slot] = make_float4(h.t, __uint_as_float(h.prim), __uint_as_float(h.tri), h.v);
+            if (store_w) st.hit_w[slot] = h.w;
+        }
+    }
+};
+
+// counters: the batch's DQueues::counters; in = index of the active count of this bounce; tail = counters + 8
+__global__ void k_tail_decide(uint32_t* counters, int in, uint32_t threshold) {
+    if (threadIdx.x == 0) {
+        uint32_t n = counters[in];
+        if (n != 0u && n <= threshold) { counters[8] = n; counters[in] = 0u; }
+        else counters[8] = 0u;
+    }
+}
+
+#ifndef BPT_TAIL_MIN_CTAS
+#define BPT_TAIL_MIN_CTAS 4
+#endif
+__global__ void __launch_bounds__(128, BPT_TAIL_MIN_CTAS)
+k_tail(DScene sc, DPathState st, BatchDesc b, uint32_t first_bounce, const uint32_t* __restrict__ in_queue,
+       const uint32_t* __restrict__ tail_count, DStats* stats) {
+    const uint32_t n = *tail_count;
+    const uint32_t i = blockIdx.x*blockDim.x + threadIdx.x;
+    if (i - (threadIdx.x & 31u) >= n) return;                   // whole warps only: the trace loop is warp-synchronous
+    bool alive = i < n;
+    TailSrc src;
+    src.st = st; src.slot = alive ? in_queue[i] : 0u;
+    src.has_shadow = src.has_closest = src.cur_shadow = false;
+    src.store_w = sc.normals != nullptr;
+    uint32_t n_rays = 0, n_shadow = 0;
+    TraceCounters ctr = {};
+    const uint32_t max_bounce = sc.settings.max_bounce_count;
+    for (uint32_t bounce = first_bounce; bounce < max_bounce; ++bounce) {
+        if (!__any_sync(0xFFFFFFFFu, alive)) break;
+        bool want_shadow = false;
+        if (alive) {
+            bool cont = false;
+            shade_path(sc, st, b, bounce, src.slot, cont, want_shadow, src.sh);
+            alive = cont;
+            n_rays += 1u + (want_shadow ? 1u : 0u);
+            n_shadow += want_shadow ? 1u : 0u;
+        }
+        src.has_shadow = want_shadow;
+        src.has_closest = alive;
+        persistent_trace<TRACE_MODE_MIXED, false, true>(sc, src, 0u, nullptr, 1u, ctr);
     }
     flush_ray_counts(stats, n_rays, n_shadow);
 }
@@ -785,7 +874,7 @@ k_trace_api(DScene sc, const bpt_ray* __restrict__ rays, uint32_t n, uint32_t ig
             const uint32_t* __restrict__ tri_original, uint32_t* cursor, uint32_t refill, DStats* stats) {
     TraceCounters ctr = {};
     ApiSrc<OCC> src = {sc, rays, out, tri_original, ignored};
-    persistent_trace<OCC ? TRACE_MODE_OCCLUSION : TRACE_MODE_CLOSEST, STATS>(sc, src, n, cursor, refill, ctr);
+    persistent_trace<OCC ? TRACE_MODE_OCCLUSION : TRACE_MODE_CLOSEST, STATS, false>(sc, src, n, cursor, refill, ctr);
     if (STATS) flush_counters(stats, ctr, OCC);
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         atomicAdd(&stats->v[0], (unsigned long long)n);

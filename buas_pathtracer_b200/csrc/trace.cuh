@@ -146,15 +146,27 @@ struct TraceCounters {   // per-thread, flushed by the caller
     uint32_t tlas_pops, instances, mesh_calls, blas_pops, blas_inner, blas_leaves, tris;
 };
 
+#ifndef BPT_PREFETCH
+#define BPT_PREFETCH 0          // 0 = off, 1 = always, 2 = only once the ray queue is exhausted (kernel tail)
+#endif
+#ifndef BPT_PREFETCH_L1
+#define BPT_PREFETCH_L1 1
+#endif
+BPT_D void prefetch_pair(const void* p) {
+#if BPT_PREFETCH_L1
+    asm volatile("prefetch.global.L1 [%0];" :: "l"(p));
+#else
+    asm volatile("prefetch.global.L2 [%0];" :: "l"(p));
+#endif
+}
+
 #define BPT_STACK_DEPTH 64     // the reference's node_stack[64] (intersection.cpp:261, :445), far children only here
 
 // Per-lane traversal state.  begin() does what precedes the reference's node loop (planes + TLAS root pop); the
 // node / triangle / instance steps are driven by persistent_trace below, which is the ONLY traversal loop in the
 // library (render passes and the bpt_trace diagnostic both run it).
 struct TraversalStack {
-    uint32_t lf[BPT_STACK_DEPTH];
-    uint32_t ca[BPT_STACK_DEPTH];
-    float    tn[BPT_STACK_DEPTH];
+    float4 e[BPT_STACK_DEPTH];     // {left_first, count|axis<<16, entry distance, -}: one STL.128 / LDL.128 per push / pop
 };
 
 // MODE: 0 = closest hit (intersect_scene), 1 = occlusion (intersect_shadow_ray), 2 = per ray (Src::load says which)
@@ -221,8 +233,10 @@ struct Traversal {
 // the phase that most of its lanes are waiting for -- ballot + popc pick it -- and "idle" is one of the phases: when
 // idle lanes are the largest group (and rays remain) they fetch new rays with one warp-aggregated atomicAdd and run
 // begin().  Every ray still performs exactly the reference's sequence of tests; only the interleaving between
-// independent rays changes.   Src supplies load(i, o, d, max_t, ignored) / store(i, hit).
-template <int MODE, bool STATS, class Src>
+// independent rays changes.   Src supplies load(i, o, d, max_t, ignored, occ) / store(i, hit).
+// LOCAL = true: there is no shared ray queue; every lane brings its own (few) rays -- Src supplies pending() /
+// next(o, d, max_t, ignored, occ) instead of load() -- and the call returns when the warp's rays are done.
+template <int MODE, bool STATS, bool LOCAL, class Src>
 BPT_D void persistent_trace(const DScene& sc, Src& src, uint32_t n, uint32_t* cursor, uint32_t refill, TraceCounters& ctr) {
     typedef Traversal<MODE, STATS> TV;
     enum { P_IDLE = 0, P_INNER = 1, P_TRI = 2, P_ITEMS = 3 };
@@ -262,17 +276,20 @@ BPT_D void persistent_trace(const DScene& sc, Src& src, uint32_t n, uint32_t* cu
             }
             if (tv.sp == 0) { finish(); return; }
             --tv.sp;
-            if (stk.tn[tv.sp] < tv.t) { tv.cur_lf = stk.lf[tv.sp]; tv.cur_ca = stk.ca[tv.sp]; classify(); return; }
+            float4 e = stk.e[tv.sp];
+            if (e.z < tv.t) { tv.cur_lf = __float_as_uint(e.x); tv.cur_ca = __float_as_uint(e.y); classify(); return; }
         }
     };
 
     for (;;) {
-        uint32_t n_inner = __popc(__ballot_sync(FULL, phase == P_INNER));
-        uint32_t n_tri   = __popc(__ballot_sync(FULL, phase == P_TRI));
-        uint32_t n_items = __popc(__ballot_sync(FULL, phase == P_ITEMS));
-        uint32_t idle_mask = __ballot_sync(FULL, phase == P_IDLE);
-        uint32_t n_idle = exhausted ? 0u : __popc(idle_mask);
-        if ((n_inner | n_tri | n_items | n_idle) == 0u) break;
+        // phase populations of the warp, one byte each, from a single warp-wide add (REDUX.SUM)
+        // (an idle lane that cannot get another ray votes for nothing)
+        bool can_fetch;
+        if constexpr (LOCAL) can_fetch = src.pending(); else can_fetch = !exhausted;
+        uint32_t counts = __reduce_add_sync(FULL, (phase == P_IDLE && !can_fetch) ? 0u : (1u << (8*phase)));
+        if (counts == 0u) break;
+        uint32_t n_inner = (counts >> 8) & 0xFFu, n_tri = (counts >> 16) & 0xFFu, n_items = counts >> 24;
+        uint32_t n_idle = counts & 0xFFu;
 
         int run = P_INNER; uint32_t best = n_inner;
         if (n_tri > best)   { best = n_tri;   run = P_TRI; }
@@ -280,6 +297,17 @@ BPT_D void persistent_trace(const DScene& sc, Src& src, uint32_t n, uint32_t* cu
         if (n_idle >= refill || n_idle > best) { run = P_IDLE; }
 
         if (run == P_IDLE) {
+          if constexpr (LOCAL) {
+            if (phase == P_IDLE && can_fetch) {
+                V3 o, d; float max_t; uint32_t ign;
+                bool is_occ = false;
+                src.next(o, d, max_t, ign, is_occ);
+                tv.occ = is_occ;
+                tv.begin(sc, o, d, max_t, ign, ctr);
+                if (tv.done()) finish(); else classify();
+            }
+          } else {
+            uint32_t idle_mask = __ballot_sync(FULL, phase == P_IDLE);
             uint32_t nid = __popc(idle_mask);
             uint32_t base = 0;
             if (lane == 0) base = atomicAdd(cursor, nid);
@@ -297,33 +325,42 @@ BPT_D void persistent_trace(const DScene& sc, Src& src, uint32_t n, uint32_t* cu
                 }
             }
             if (base + nid >= n) exhausted = true;
+          }
         } else if (run == P_INNER) {
           // stay in this phase while at least 3/4 of the lanes that started it still want it (1 vote instead of 4)
           uint32_t keep = max(best - (best >> 2), 1u);
           do {
             if (phase == P_INNER) {
-                const DNodeHalf* pr = tv.nodes + tv.cur_lf;
-                float4 l0 = __ldg(&pr[0].q0), l1 = __ldg(&pr[0].q1);
-                float4 r0 = __ldg(&pr[1].q0), r1 = __ldg(&pr[1].q1);
-                float tnl, tnr;
-                bool hl, hr;
+                // the parent's split axis and the ray's sign say which child is near (intersection.cpp:303-318):
+                // fetch them in that order so nothing has to be swapped afterwards
+                uint32_t right_first = (tv.ray.neg >> (tv.cur_ca >> 16)) & 1u;
+                const DNodeHalf* pn = tv.nodes + (tv.cur_lf + right_first);
+                const DNodeHalf* pf = tv.nodes + (tv.cur_lf + (right_first ^ 1u));
+                float4 n0 = __ldg(&pn->q0), n1 = __ldg(&pn->q1);
+                float4 f0 = __ldg(&pf->q0), f1 = __ldg(&pf->q1);
+#if BPT_PREFETCH
+                // the children's own child pairs are known as soon as the records arrive: start pulling the next
+                // step's record towards the SM while this step's slab tests run (an inner child has count == 0)
+                if (BPT_PREFETCH == 1 || exhausted) {
+                    if ((__float_as_uint(n1.w) & 0xFFFFu) == 0u) prefetch_pair(tv.nodes + __float_as_uint(n1.z));
+                    if ((__float_as_uint(f1.w) & 0xFFFFu) == 0u) prefetch_pair(tv.nodes + __float_as_uint(f1.z));
+                }
+#endif
+                float near_tn, far_tn;
+                bool near_hit, far_hit;
                 if (tame && (tv.ray.neg & BPT_RAY_TAME)) {
-                    hl = slab_test_tame(tv.ray, l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, tnl);
-                    hr = slab_test_tame(tv.ray, r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, tnr);
+                    near_hit = slab_test_tame(tv.ray, n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, near_tn);
+                    far_hit  = slab_test_tame(tv.ray, f0.x, f0.y, f0.z, f0.w, f1.x, f1.y, far_tn);
                 } else {
-                    hl = slab_test(tv.ray, l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, tnl);
-                    hr = slab_test(tv.ray, r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, tnr);
-                    hl = hl && parallel_axes_may_contain(tv.ray, l0.x, l0.y, l0.z, l0.w, l1.x, l1.y);
-                    hr = hr && parallel_axes_may_contain(tv.ray, r0.x, r0.y, r0.z, r0.w, r1.x, r1.y);
+                    near_hit = slab_test(tv.ray, n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, near_tn);
+                    far_hit  = slab_test(tv.ray, f0.x, f0.y, f0.z, f0.w, f1.x, f1.y, far_tn);
+                    near_hit = near_hit && parallel_axes_may_contain(tv.ray, n0.x, n0.y, n0.z, n0.w, n1.x, n1.y);
+                    far_hit  = far_hit  && parallel_axes_may_contain(tv.ray, f0.x, f0.y, f0.z, f0.w, f1.x, f1.y);
                 }
                 if (STATS) { if (tv.level) { tv.c_pops += 2; tv.c_inner += 1; } else ctr.tlas_pops += 2; }
-                bool right_first = (tv.ray.neg >> (tv.cur_ca >> 16)) & 1u;
-                bool  near_hit = right_first ? hr : hl,            far_hit = right_first ? hl : hr;
-                float near_tn  = right_first ? tnr : tnl,          far_tn  = right_first ? tnl : tnr;
-                uint32_t near_lf = __float_as_uint(right_first ? r1.z : l1.z), far_lf = __float_as_uint(right_first ? l1.z : r1.z);
-                uint32_t near_ca = __float_as_uint(right_first ? r1.w : l1.w), far_ca = __float_as_uint(right_first ? l1.w : r1.w);
+                uint32_t near_lf = __float_as_uint(n1.z), near_ca = __float_as_uint(n1.w);
                 if (far_hit && tv.sp < BPT_STACK_DEPTH) {
-                    stk.lf[tv.sp] = far_lf; stk.ca[tv.sp] = far_ca; stk.tn[tv.sp] = far_tn; ++tv.sp;
+                    stk.e[tv.sp] = make_float4(f1.z, f1.w, far_tn, 0.0f); ++tv.sp;
                 }
                 if (near_hit && near_tn < tv.t) { tv.cur_lf = near_lf; tv.cur_ca = near_ca; classify(); }
                 else pop();

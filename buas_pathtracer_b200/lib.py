@@ -14,7 +14,7 @@ _LIB = None
 DEVICE_SYMBOLS = [
     "create", "destroy", "set_sampler_tables", "upload_scene", "update_settings", "film_resize", "film_clear",
     "film_use_external", "film_device_ptr", "download_film", "render_pass", "render_pass_bands", "sync", "trace", "set_sample_records",
-    "stats_enable", "get_stats", "get_pass_timing", "set_detailed_timing", "get_transfer_bytes", "resolve_bgra8",
+    "stats_enable", "get_stats", "get_pass_timing", "set_detailed_timing", "set_tail_threshold", "get_transfer_bytes", "resolve_bgra8",
 ]
 MISC_SYMBOLS = ["last_error", "version", "make_displaced_icosphere", "make_procedural_skydome"]
 
@@ -91,6 +91,8 @@ def load_library():
     L.bpt_get_pass_timing.argtypes = [vp, P(capi.PassTiming)]
     L.bpt_set_detailed_timing.restype = C.c_int
     L.bpt_set_detailed_timing.argtypes = [vp, C.c_int]
+    L.bpt_set_tail_threshold.restype = C.c_int
+    L.bpt_set_tail_threshold.argtypes = [vp, C.c_uint32]
     L.bpt_get_transfer_bytes.restype = C.c_int
     L.bpt_get_transfer_bytes.argtypes = [vp, P(C.c_uint64), P(C.c_uint64), C.c_int]
     L.bpt_resolve_bgra8.restype = C.c_int
@@ -226,6 +228,9 @@ class Renderer:
 
     def set_detailed_timing(self, on=True):
         _check(self.lib.bpt_set_detailed_timing(self.handle, int(on)), "bpt_set_detailed_timing")
+
+    def set_tail_threshold(self, paths):
+        _check(self.lib.bpt_set_tail_threshold(self.handle, int(paths)), "bpt_set_tail_threshold")
 
     def transfer_bytes(self, reset=False):
         a, b = C.c_uint64(), C.c_uint64()

@@ -154,12 +154,27 @@ def _render_both(renderer, pair, w, h, spp, salt=0, frame_count=0):
     a, b = pair
     renderer.upload_scene(a)
     renderer.film_resize(w, h)
+    # two schedules of the same work: pure wavefront (one round of launches per bounce) and the default, which hands
+    # the last survivors of a batch to the fused k_tail launch.  Per path they execute the same operations in the
+    # same order, so the per-sample records must agree bit for bit; the reference is then compared with the default.
+    renderer.set_tail_threshold(0)
+    rec0 = renderer.attach_records(w * h * spp)
+    renderer.render_pass(spp, frame_count=frame_count, salt=salt)
+    renderer.sync()
+    rec0 = rec0.copy()
+    renderer.attach_records(0)
+    renderer.set_tail_threshold(32768)
+    renderer.film_clear()
     rec = renderer.attach_records(w * h * spp)
     renderer.render_pass(spp, frame_count=frame_count, salt=salt)
     film = renderer.download_film()
     renderer.attach_records(0)
+    rec = rec.copy()
+    for k in ("radiance", "ray_o", "ray_d", "rays"):
+        assert np.array_equal(bits(rec0[k]) if rec0[k].dtype == np.float32 else rec0[k],
+                              bits(rec[k]) if rec[k].dtype == np.float32 else rec[k]), f"wavefront vs fused tail: {k} differs"
     rfilm, rrec = b.render_parity(w, h, spp, frame_count=frame_count, salt=salt, records=True)
-    return film, rec.copy(), rfilm, rrec
+    return film, rec, rfilm, rrec
 
 
 def _check_records(rec, rrec, what):
