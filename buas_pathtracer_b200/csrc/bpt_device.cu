@@ -66,7 +66,8 @@ struct bpt_ctx {
     } pipes[BPT_MAX_PIPES];
     int n_pipes = 2;
     uint32_t min_batches = 0;             // experiment knob (BPT_MIN_BATCHES): at least this many batches per pass
-    uint32_t tail_threshold = 32768;      // paths: at or below this many survivors a batch finishes inside k_tail (0 = never)
+    uint32_t tail_threshold = 65536;      // paths: at or below this many survivors a batch finishes inside k_tail (0 = never)
+    uint32_t tail_refill = 8;             // k_tail: idle lanes shade / start their next ray once this many wait (or they are the largest group)
     bool merge_traces = true;             // trace bounce b's extension rays and bounce b-1's shadow rays in one launch
     int32_t* d_row_map = nullptr;
     uint32_t row_map_capacity = 0;
@@ -232,6 +233,7 @@ int bpt_create(int device, bpt_ctx** out_ctx) {
     }
     if (const char* e = getenv("BPT_REFILL")) { int v = atoi(e); if (v >= 1 && v <= 33) ctx->refill = (uint32_t)v; }
     if (const char* e = getenv("BPT_MERGE_TRACES")) ctx->merge_traces = atoi(e) != 0;
+    if (const char* e = getenv("BPT_TAIL_REFILL")) { int v = atoi(e); if (v >= 1 && v <= 33) ctx->tail_refill = (uint32_t)v; }
     if (const char* e = getenv("BPT_TAIL_THRESHOLD")) { long v = atol(e); if (v >= 0 && v <= (1 << 22)) ctx->tail_threshold = (uint32_t)v; }
     if (const char* e = getenv("BPT_PIPES")) { int v = atoi(e); if (v >= 1 && v <= BPT_MAX_PIPES) ctx->n_pipes = v; }
     if (const char* e = getenv("BPT_MIN_BATCHES")) { int v = atoi(e); if (v >= 1 && v <= 64) ctx->min_batches = (uint32_t)v; }
@@ -698,7 +700,7 @@ retry_shape:
                     // few survivors: finish them inside one launch; the wavefront launches below then find empty queues
                     k_tail_decide<<<1, 32, 0, s>>>(counters, in, ctx->tail_threshold);
                     begin_span(ctx, ST_TRACE, s);
-                    k_tail<<<(ctx->tail_threshold + 127)/128, 128, 0, s>>>(sc, pp.st, b, bounce, pp.q.active[in], counters + 8, ctx->d_stats);
+                    k_tail<<<(ctx->tail_threshold + 127)/128, 128, 0, s>>>(sc, pp.st, b, bounce, pp.q.active[in], counters + 8, ctx->tail_refill, ctx->d_stats);
                     end_span(ctx, s);
                     ctx->launches += 2; ctx->trace_launches++;
                 }

@@ -662,18 +662,32 @@ k_shade(DScene sc, DPathState st, BatchDesc b, uint32_t bounce,
 // ---------------------------------------------------------------------------------------------------------------
 // Fused tail.  Once only a few paths of a batch are still alive, a wavefront bounce costs the latency of its longest
 // ray four launches over (the machine is empty), bounce after bounce.  k_tail_decide (one thread, between the trace
-// and the shade of a bounce) hands the survivors over when they fit: it moves the active count to tail[0] and zeroes
-// it, so the remaining wavefront launches of the batch find empty queues.  k_tail then carries each surviving path to
-// its end inside ONE launch: lane = path; per bounce shade_path (the same function k_shade runs), then the lane's
-// own shadow ray and extension ray through persistent_trace in LOCAL mode.  Per path the sequence of operations --
-// and of float additions into its radiance -- is the one the wavefront would have executed.
+// and the shade of a bounce) hands the survivors over when they fit: it moves the active count to counters[8] and
+// zeroes it, so the remaining wavefront launches of the batch find empty queues.  k_tail then carries each surviving
+// path to its end inside ONE launch: lane = path, and shading is simply what an idle lane does to get its next rays
+// (persistent_trace in LOCAL mode): shade_path -- the same function k_shade runs -- then the lane's shadow ray, then
+// its extension ray, then shade again ...  No lane waits for another path's bounce.  Per path the sequence of
+// operations, and of float additions into its radiance, is the one the wavefront would have executed.
 struct TailSrc {
+    const DScene* sc;
+    const BatchDesc* b;
     DPathState st;
     DShadowItem sh;
-    uint32_t slot;
+    uint32_t slot, bounce;
+    uint32_t n_rays, n_shadow;
+    bool alive;                  // the path's current extension ray has been traced and wants shading
     bool has_shadow, has_closest, cur_shadow, store_w;
-    BPT_D bool pending() const { return has_shadow || has_closest; }
-    BPT_D void next(V3& o, V3& d, float& max_t, uint32_t& ignored, bool& occ) {
+    BPT_D bool pending() const { return has_shadow || has_closest || alive; }
+    BPT_D bool next(V3& o, V3& d, float& max_t, uint32_t& ignored, bool& occ) {
+        if (!has_shadow && !has_closest) {
+            bool cont = false, want_shadow = false;
+            shade_path(*sc, st, *b, bounce, slot, cont, want_shadow, sh);
+            n_rays += 1u + (want_shadow ? 1u : 0u);
+            n_shadow += want_shadow ? 1u : 0u;
+            ++bounce;
+            has_shadow = want_shadow; has_closest = cont; alive = cont;
+            if (!want_shadow && !cont) return false;
+        }
         if (has_shadow) {
             o = v3(sh.o_maxt); d = v3(sh.d_light); max_t = sh.o_maxt.w; ignored = __float_as_uint(sh.d_light.w);
             occ = true; has_shadow = false; cur_shadow = true;
@@ -682,6 +696,7 @@ struct TailSrc {
             o = v3(ro); d = v3(rd); max_t = ro.w; ignored = 0u;
             occ = false; has_closest = false; cur_shadow = false;
         }
+        return true;
     }
     BPT_D void store(uint32_t, const HitRecord& h) const {
         if (cur_shadow) {
@@ -697,7 +712,7 @@ struct TailSrc {
     }
 };
 
-// counters: the batch's DQueues::counters; in = index of the active count of this bounce; tail = counters + 8
+// counters: the batch's DQueues::counters; in = index of the active count of this bounce
 __global__ void k_tail_decide(uint32_t* counters, int in, uint32_t threshold) {
     if (threadIdx.x == 0) {
         uint32_t n = counters[in];
@@ -711,33 +726,21 @@ __global__ void k_tail_decide(uint32_t* counters, int in, uint32_t threshold) {
 #endif
 __global__ void __launch_bounds__(128, BPT_TAIL_MIN_CTAS)
 k_tail(DScene sc, DPathState st, BatchDesc b, uint32_t first_bounce, const uint32_t* __restrict__ in_queue,
-       const uint32_t* __restrict__ tail_count, DStats* stats) {
+       const uint32_t* __restrict__ tail_count, uint32_t refill, DStats* stats) {
     const uint32_t n = *tail_count;
     const uint32_t i = blockIdx.x*blockDim.x + threadIdx.x;
     if (i - (threadIdx.x & 31u) >= n) return;                   // whole warps only: the trace loop is warp-synchronous
-    bool alive = i < n;
     TailSrc src;
-    src.st = st; src.slot = alive ? in_queue[i] : 0u;
+    src.sc = &sc; src.b = &b; src.st = st;
+    src.alive = i < n;
+    src.slot = src.alive ? in_queue[i] : 0u;
+    src.bounce = first_bounce;
+    src.n_rays = src.n_shadow = 0u;
     src.has_shadow = src.has_closest = src.cur_shadow = false;
     src.store_w = sc.normals != nullptr;
-    uint32_t n_rays = 0, n_shadow = 0;
     TraceCounters ctr = {};
-    const uint32_t max_bounce = sc.settings.max_bounce_count;
-    for (uint32_t bounce = first_bounce; bounce < max_bounce; ++bounce) {
-        if (!__any_sync(0xFFFFFFFFu, alive)) break;
-        bool want_shadow = false;
-        if (alive) {
-            bool cont = false;
-            shade_path(sc, st, b, bounce, src.slot, cont, want_shadow, src.sh);
-            alive = cont;
-            n_rays += 1u + (want_shadow ? 1u : 0u);
-            n_shadow += want_shadow ? 1u : 0u;
-        }
-        src.has_shadow = want_shadow;
-        src.has_closest = alive;
-        persistent_trace<TRACE_MODE_MIXED, false, true>(sc, src, 0u, nullptr, 1u, ctr);
-    }
-    flush_ray_counts(stats, n_rays, n_shadow);
+    persistent_trace<TRACE_MODE_MIXED, false, true>(sc, src, 0u, nullptr, refill, ctr);
+    flush_ray_counts(stats, src.n_rays, src.n_shadow);
 }
 
 // render_tile's tail (raytracer.cpp:469-488) + splat_filter (:187-259): one thread per pixel of the batch walks that

@@ -234,8 +234,9 @@ struct Traversal {
 // idle lanes are the largest group (and rays remain) they fetch new rays with one warp-aggregated atomicAdd and run
 // begin().  Every ray still performs exactly the reference's sequence of tests; only the interleaving between
 // independent rays changes.   Src supplies load(i, o, d, max_t, ignored, occ) / store(i, hit).
-// LOCAL = true: there is no shared ray queue; every lane brings its own (few) rays -- Src supplies pending() /
-// next(o, d, max_t, ignored, occ) instead of load() -- and the call returns when the warp's rays are done.
+// LOCAL = true: there is no shared ray queue; every lane produces its own rays -- Src supplies pending() and
+// bool next(o, d, max_t, ignored, occ) instead of load(); next() may do arbitrary per-lane work (k_tail shades the
+// lane's path there) -- and the call returns when no lane has anything pending.
 template <int MODE, bool STATS, bool LOCAL, class Src>
 BPT_D void persistent_trace(const DScene& sc, Src& src, uint32_t n, uint32_t* cursor, uint32_t refill, TraceCounters& ctr) {
     typedef Traversal<MODE, STATS> TV;
@@ -301,10 +302,11 @@ BPT_D void persistent_trace(const DScene& sc, Src& src, uint32_t n, uint32_t* cu
             if (phase == P_IDLE && can_fetch) {
                 V3 o, d; float max_t; uint32_t ign;
                 bool is_occ = false;
-                src.next(o, d, max_t, ign, is_occ);
-                tv.occ = is_occ;
-                tv.begin(sc, o, d, max_t, ign, ctr);
-                if (tv.done()) finish(); else classify();
+                if (src.next(o, d, max_t, ign, is_occ)) {       // false: the lane's path ended without another ray
+                    tv.occ = is_occ;
+                    tv.begin(sc, o, d, max_t, ign, ctr);
+                    if (tv.done()) finish(); else classify();
+                }
             }
           } else {
             uint32_t idle_mask = __ballot_sync(FULL, phase == P_IDLE);

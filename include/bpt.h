@@ -325,7 +325,7 @@ BPT_API int bpt_get_pass_timing(bpt_ctx* ctx, bpt_pass_timing* out);
 BPT_API int bpt_set_detailed_timing(bpt_ctx* ctx, int enable);
 /* Scheduling knob (results do not depend on it): once at most `paths` paths of a batch survive, they finish inside one
  * fused launch instead of one wavefront round per bounce (the analogue of a render_tile worker simply looping on,
- * raytracer.cpp:409-494).  0 = always wavefront.  Default 32768. */
+ * raytracer.cpp:409-494).  0 = always wavefront.  Default 65536. */
 BPT_API int bpt_set_tail_threshold(bpt_ctx* ctx, uint32_t paths);
 /* cumulative bytes this context copied host->device / device->host (scene uploads, rays, film, records) */
 BPT_API int bpt_get_transfer_bytes(bpt_ctx* ctx, uint64_t* h2d, uint64_t* d2h, int reset);

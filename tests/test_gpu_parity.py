@@ -163,7 +163,7 @@ def _render_both(renderer, pair, w, h, spp, salt=0, frame_count=0):
     renderer.sync()
     rec0 = rec0.copy()
     renderer.attach_records(0)
-    renderer.set_tail_threshold(32768)
+    renderer.set_tail_threshold(65536)
     renderer.film_clear()
     rec = renderer.attach_records(w * h * spp)
     renderer.render_pass(spp, frame_count=frame_count, salt=salt)
