@@ -68,7 +68,8 @@ struct bpt_ctx {
     uint32_t min_batches = 0;             // experiment knob (BPT_MIN_BATCHES): at least this many batches per pass
     uint32_t tail_threshold = 65536;      // paths: at or below this many survivors a batch finishes inside k_tail (0 = never)
     uint32_t tail_refill = 8;             // k_tail: idle lanes shade / start their next ray once this many wait (or they are the largest group)
-    bool merge_traces = true;             // trace bounce b's extension rays and bounce b-1's shadow rays in one launch
+    bool merge_traces = true;
+    uint32_t merge_max_slots = 16u << 20; // batches larger than this trace the two populations separately             // trace bounce b's extension rays and bounce b-1's shadow rays in one launch
     int32_t* d_row_map = nullptr;
     uint32_t row_map_capacity = 0;
 
@@ -172,6 +173,16 @@ void end_span(bpt_ctx* ctx, cudaStream_t stream) {
     ctx->spans_used++;
 }
 
+// BPT_DEBUG_SYNC=1: synchronise after every launch of a pass and say which kernel it was (finding a hung launch)
+void debug_sync(const char* what, uint32_t bounce, cudaStream_t s) {
+    static int on = -1;
+    if (on < 0) { const char* e = getenv("BPT_DEBUG_SYNC"); on = (e && atoi(e)) ? 1 : 0; }
+    if (!on) return;
+    fprintf(stderr, "launch %s bounce %u ...", what, bounce); fflush(stderr);
+    cudaError_t e = cudaStreamSynchronize(s);
+    fprintf(stderr, " %s\n", cudaGetErrorString(e)); fflush(stderr);
+}
+
 uint32_t grid_for(const bpt_ctx* ctx, uint64_t work, uint32_t threads, uint32_t ctas_per_sm) {
     uint64_t need = (work + threads - 1)/threads;
     uint64_t cap = (uint64_t)ctx->sm_count*ctas_per_sm;
@@ -233,6 +244,7 @@ int bpt_create(int device, bpt_ctx** out_ctx) {
     }
     if (const char* e = getenv("BPT_REFILL")) { int v = atoi(e); if (v >= 1 && v <= 33) ctx->refill = (uint32_t)v; }
     if (const char* e = getenv("BPT_MERGE_TRACES")) ctx->merge_traces = atoi(e) != 0;
+    if (const char* e = getenv("BPT_MERGE_MAX_SLOTS")) { long long v = atoll(e); if (v >= 0 && v <= 0x7FFFFFFFll) ctx->merge_max_slots = (uint32_t)v; }
     if (const char* e = getenv("BPT_TAIL_REFILL")) { int v = atoi(e); if (v >= 1 && v <= 33) ctx->tail_refill = (uint32_t)v; }
     if (const char* e = getenv("BPT_TAIL_THRESHOLD")) { long v = atol(e); if (v >= 0 && v <= (1 << 22)) ctx->tail_threshold = (uint32_t)v; }
     if (const char* e = getenv("BPT_PIPES")) { int v = atoi(e); if (v >= 1 && v <= BPT_MAX_PIPES) ctx->n_pipes = v; }
@@ -673,7 +685,10 @@ retry_shape:
             // counters: [0]/[1] = active-queue sizes (ping-pong), [2] = shadow count, [3] = fetch cursor.
             // With the counting instantiations (stats) the two populations are traced by separate launches.
             // Per-kernel timing: ST_TRACE spans k_trace_closest (bounce 0) + k_trace_merged, ST_SHADOW the final k_trace_shadow.
-            const bool merged = !stats && ctx->merge_traces;
+            // Merging pays where kernel tails dominate (small batches: +14 % on an 8-rank share of C2) and costs where
+            // they do not (C4 at 64 Mi slots: -15 %, the mixed population diverges more): merge below a batch size.
+            const bool merged = !stats && ctx->merge_traces && b.slots <= ctx->merge_max_slots;
+            const bool tail = !stats && ctx->tail_threshold > 0;
             for (uint32_t bounce = 0; bounce < max_bounce; ++bounce) {
                 int in = bounce & 1, out = in ^ 1;
                 const uint32_t* in_queue = bounce == 0 ? nullptr : pp.q.active[in];
@@ -686,9 +701,11 @@ retry_shape:
                 begin_span(ctx, ST_TRACE, s);
                 if (merged && bounce > 0) {
                     k_trace_merged<<<tg, 128, 0, s>>>(sc, pp.st, in_queue, in_count, pp.q.shadow, counters + 2, counters + 3, ctx->refill);
+                    debug_sync("k_trace_merged", bounce, s);
                 } else {
                     if (stats) k_trace_closest<true ><<<tg, 128, 0, s>>>(sc, pp.st, in_queue, in_count, b.slots, counters + 3, ctx->refill, ctx->d_stats);
                     else       k_trace_closest<false><<<tg, 128, 0, s>>>(sc, pp.st, in_queue, in_count, b.slots, counters + 3, ctx->refill, ctx->d_stats);
+                    debug_sync("k_trace_closest", bounce, s);
                 }
                 end_span(ctx, s);
                 ctx->launches++; ctx->trace_launches++;
@@ -696,17 +713,19 @@ retry_shape:
                 // the shadow items of the previous bounce are consumed (merged) or not yet produced: reset before shading
                 k_reset_counters<<<1, 32, 0, s>>>(counters, (1 << out) | (1 << 2));
                 ctx->launches++;
-                if (merged && bounce > 0 && ctx->tail_threshold > 0) {
+                if (tail && bounce > 0) {
                     // few survivors: finish them inside one launch; the wavefront launches below then find empty queues
                     k_tail_decide<<<1, 32, 0, s>>>(counters, in, ctx->tail_threshold);
                     begin_span(ctx, ST_TRACE, s);
                     k_tail<<<(ctx->tail_threshold + 127)/128, 128, 0, s>>>(sc, pp.st, b, bounce, pp.q.active[in], counters + 8, ctx->tail_refill, ctx->d_stats);
+                    debug_sync("k_tail", bounce, s);
                     end_span(ctx, s);
                     ctx->launches += 2; ctx->trace_launches++;
                 }
                 begin_span(ctx, ST_SHADE, s);
                 k_shade<<<grid_for(ctx, work, 128, 16), 128, 0, s>>>(sc, pp.st, b, bounce, in_queue, in_count, b.slots,
                                                                     pp.q.active[out], counters + out, pp.q.shadow, counters + 2, ctx->d_stats);
+                debug_sync("k_shade", bounce, s);
                 end_span(ctx, s);
                 ctx->launches++;
 
@@ -714,6 +733,7 @@ retry_shape:
                     begin_span(ctx, ST_SHADOW, s);
                     if (stats) k_trace_shadow<true ><<<tg, 128, 0, s>>>(sc, pp.st, pp.q.shadow, counters + 2, counters + 4, ctx->refill, ctx->d_stats);
                     else       k_trace_shadow<false><<<tg, 128, 0, s>>>(sc, pp.st, pp.q.shadow, counters + 2, counters + 4, ctx->refill, ctx->d_stats);
+                    debug_sync("k_trace_shadow", bounce, s);
                     end_span(ctx, s);
                     ctx->launches++; ctx->trace_launches++;
                 }
@@ -823,6 +843,16 @@ int bpt_resolve_bgra8(bpt_ctx* ctx, const bpt_post_settings* post, const uint8_t
     cudaFree(d_out); cudaFree(d_dither);
     if (e != cudaSuccess) { set_error("bpt_resolve_bgra8: %s", cudaGetErrorString(e)); return BPT_ERR_CUDA; }
     ctx->d2h_bytes += n*sizeof(uint32_t);
+    return BPT_OK;
+}
+
+// debugging aid (not part of include/bpt.h): copy a pipeline's 16 queue counters out on a side stream while a pass runs
+extern "C" __attribute__((visibility("default"))) int bpt_debug_peek_counters(bpt_ctx* ctx, int pipe, uint32_t* out16) {
+    if (!ctx || pipe < 0 || pipe >= BPT_MAX_PIPES || !ctx->pipes[pipe].q.counters) return BPT_ERR_ARG;
+    static cudaStream_t side = nullptr;
+    if (!side) cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking);
+    if (cudaMemcpyAsync(out16, ctx->pipes[pipe].q.counters, 64, cudaMemcpyDeviceToHost, side) != cudaSuccess) return BPT_ERR_CUDA;
+    if (cudaStreamSynchronize(side) != cudaSuccess) return BPT_ERR_CUDA;
     return BPT_OK;
 }
 

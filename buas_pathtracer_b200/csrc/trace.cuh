@@ -146,20 +146,6 @@ struct TraceCounters {   // per-thread, flushed by the caller
     uint32_t tlas_pops, instances, mesh_calls, blas_pops, blas_inner, blas_leaves, tris;
 };
 
-#ifndef BPT_PREFETCH
-#define BPT_PREFETCH 0          // 0 = off, 1 = always, 2 = only once the ray queue is exhausted (kernel tail)
-#endif
-#ifndef BPT_PREFETCH_L1
-#define BPT_PREFETCH_L1 1
-#endif
-BPT_D void prefetch_pair(const void* p) {
-#if BPT_PREFETCH_L1
-    asm volatile("prefetch.global.L1 [%0];" :: "l"(p));
-#else
-    asm volatile("prefetch.global.L2 [%0];" :: "l"(p));
-#endif
-}
-
 #define BPT_STACK_DEPTH 64     // the reference's node_stack[64] (intersection.cpp:261, :445), far children only here
 
 // Per-lane traversal state.  begin() does what precedes the reference's node loop (planes + TLAS root pop); the
@@ -282,7 +268,12 @@ BPT_D void persistent_trace(const DScene& sc, Src& src, uint32_t n, uint32_t* cu
         }
     };
 
-    for (;;) {
+    // The scheduling loop.  Its trip count is bounded on purpose: with a plain `for (;;)` whose only exit is the vote
+    // below, nvcc 12.9 rotates the loop and peels its first iteration, and the resulting k_trace_merged hung on
+    // B200 (deterministically, BASELINE config 4 at >= 16 spp: launch of bounce 3 never returned; every
+    // instrumented build ran through).  A second, never-taken exit at the loop head keeps the loop in its source
+    // shape; tests/test_gpu_golden_and_fullsize.py::test_no_hang_* pins the behaviour.
+    for (unsigned long long trips = 0; trips != ~0ull; ++trips) {
         // phase populations of the warp, one byte each, from a single warp-wide add (REDUX.SUM)
         // (an idle lane that cannot get another ray votes for nothing)
         bool can_fetch;
@@ -340,14 +331,6 @@ BPT_D void persistent_trace(const DScene& sc, Src& src, uint32_t n, uint32_t* cu
                 const DNodeHalf* pf = tv.nodes + (tv.cur_lf + (right_first ^ 1u));
                 float4 n0 = __ldg(&pn->q0), n1 = __ldg(&pn->q1);
                 float4 f0 = __ldg(&pf->q0), f1 = __ldg(&pf->q1);
-#if BPT_PREFETCH
-                // the children's own child pairs are known as soon as the records arrive: start pulling the next
-                // step's record towards the SM while this step's slab tests run (an inner child has count == 0)
-                if (BPT_PREFETCH == 1 || exhausted) {
-                    if ((__float_as_uint(n1.w) & 0xFFFFu) == 0u) prefetch_pair(tv.nodes + __float_as_uint(n1.z));
-                    if ((__float_as_uint(f1.w) & 0xFFFFu) == 0u) prefetch_pair(tv.nodes + __float_as_uint(f1.z));
-                }
-#endif
                 float near_tn, far_tn;
                 bool near_hit, far_hit;
                 if (tame && (tv.ray.neg & BPT_RAY_TAME)) {

@@ -125,3 +125,26 @@ def test_c2_full_size_properties(renderer, c2_full):
     renderer.render_pass(32, frame_count=32)
     halves = renderer.download_film()
     assert np.allclose(full, halves, rtol=1e-4, atol=1e-5)
+
+
+# --- liveness -------------------------------------------------------------------------------------------------------
+# A build of the traversal loop once hung on exactly these workloads (k_trace_merged, BASELINE config 4 at >= 16 spp and
+# config 3 at 256 spp; see the comment on the scheduling loop in csrc/trace.cuh).  Each case runs in a child process
+# under a timeout so that a regression fails here instead of hanging the suite; the forced-merge cases put the
+# merged kernel on batch sizes the default policy would trace unmerged.
+@pytest.mark.parametrize("config,spp,env", [
+    ("c4", 16, {}),
+    ("c4", 32, {"BPT_MERGE_MAX_SLOTS": "2000000000"}),
+    ("c4", 32, {"BPT_TAIL_THRESHOLD": "0", "BPT_MERGE_MAX_SLOTS": "2000000000"}),
+    ("c3", 32, {"BPT_MERGE_MAX_SLOTS": "2000000000"}),
+    ("c2", 16, {"BPT_MERGE_MAX_SLOTS": "2000000000", "BPT_TAIL_THRESHOLD": "4000000"}),
+])
+def test_no_hang_full_frame(config, spp, env):
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, os.path.join(root, "tools", "profile_pass.py"), "--config", config, "--spp", str(spp),
+           "--passes", "2", "--no-detail"]
+    p = subprocess.run(cmd, env=dict(os.environ, **env), stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True,
+                       timeout=150)
+    assert p.returncode == 0, p.stdout[-2000:]
+    assert "Mrays/s" in p.stdout
