@@ -321,7 +321,7 @@ def main():
     closest_rays = st_counts.rays - st_counts.shadow_rays
     trav_ms = trace_ms + shadow_ms
     achieved = (bytes_closest + bytes_shadow) / (trav_ms * 1e-3) / 1e9 if trav_ms > 0 else None
-    roofline = {"bound": "hbm", "kernel": "persistent_trace (k_trace_closest + k_trace_merged + k_trace_shadow launches)",
+    roofline = {"bound": "hbm", "kernel": "persistent_trace (all k_trace_closest / k_trace_shadow / k_trace_merged / k_tail launches of a pass)",
                 "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": (achieved / peak) if achieved else None, "traffic": None, "peak_source": peak_src,
                 "algorithmic_bytes_per_ray": (bytes_closest + bytes_shadow) / max(1, st_counts.rays),
@@ -330,8 +330,8 @@ def main():
                 "shadow_bytes_per_ray": bytes_shadow / max(1, st_counts.shadow_rays),
                 "kernel_ms_per_step": trav_ms, "launches_per_step": trace_launches,
                 "avg_launch_ms": trav_ms / max(1, trace_launches),
-                "stage_ms_per_step": {"raygen": raygen_ms, "trace_closest_and_merged": trace_ms, "shade": shade_ms,
-                                      "trace_shadow_last_bounce": shadow_ms, "splat": splat_ms}}
+                "stage_ms_per_step": {"raygen": raygen_ms, "trace_closest_merged_tail": trace_ms, "shade": shade_ms,
+                                      "trace_shadow": shadow_ms, "splat": splat_ms}}
     traffic_file = os.path.join(ROOT, "profiles", "trace_dram_bytes.json")
     if os.path.exists(traffic_file):
         tf = json.load(open(traffic_file))

@@ -846,16 +846,6 @@ int bpt_resolve_bgra8(bpt_ctx* ctx, const bpt_post_settings* post, const uint8_t
     return BPT_OK;
 }
 
-// debugging aid (not part of include/bpt.h): copy a pipeline's 16 queue counters out on a side stream while a pass runs
-extern "C" __attribute__((visibility("default"))) int bpt_debug_peek_counters(bpt_ctx* ctx, int pipe, uint32_t* out16) {
-    if (!ctx || pipe < 0 || pipe >= BPT_MAX_PIPES || !ctx->pipes[pipe].q.counters) return BPT_ERR_ARG;
-    static cudaStream_t side = nullptr;
-    if (!side) cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking);
-    if (cudaMemcpyAsync(out16, ctx->pipes[pipe].q.counters, 64, cudaMemcpyDeviceToHost, side) != cudaSuccess) return BPT_ERR_CUDA;
-    if (cudaStreamSynchronize(side) != cudaSuccess) return BPT_ERR_CUDA;
-    return BPT_OK;
-}
-
 int bpt_set_tail_threshold(bpt_ctx* ctx, uint32_t paths) {
     if (!ctx) { set_error("bpt_set_tail_threshold: null ctx"); return BPT_ERR_ARG; }
     if (paths > (1u << 22)) { set_error("bpt_set_tail_threshold: at most %u paths", 1u << 22); return BPT_ERR_ARG; }
