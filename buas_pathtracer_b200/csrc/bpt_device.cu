@@ -574,9 +574,13 @@ static int render_rows(bpt_ctx* ctx, int32_t x0, int32_t x1, const std::vector<i
     if (seed_mode != BPT_SEED_PER_PIXEL) { set_error("%s: unknown seed mode", who); return BPT_ERR_ARG; }
     if (x0 < 0 || x1 > (int32_t)ctx->film_w || x0 >= x1 || rows.empty() || spp == 0) { set_error("%s: bad rect/spp", who); return BPT_ERR_ARG; }
     for (int32_t y : rows) if (y < 0 || y >= (int32_t)ctx->film_h) { set_error("%s: bad rect/spp (row %d)", who, y); return BPT_ERR_ARG; }
-    if (ctx->sc.settings.integrator != BPT_INTEGRATOR_ADVANCED) {
-        set_error("%s: only the \"Advanced Pathtracer\" integrator runs on the device (SURVEY 8a5)", who);
-        return BPT_ERR_UNSUPPORTED;
+    {
+        int ig = ctx->sc.settings.integrator;
+        if (ig == BPT_INTEGRATOR_WHITTED || ig == BPT_INTEGRATOR_GT_RECURSIVE) {
+            // the two recursive integrators (integrators.cpp:310-484) are not built; refuse rather than substitute
+            set_error("%s: the \"Whitted\" and \"Ground Truth Recursive\" integrators do not run on the device (SURVEY 8f rank 4)", who);
+            return BPT_ERR_UNSUPPORTED;
+        }
     }
     if (ctx->sc.filter_lut_size != 0 && ctx->sc.filter_radius == 0) { set_error("%s: filter LUT with radius 0", who); return BPT_ERR_ARG; }
     CK(cudaSetDevice(ctx->device));
@@ -660,6 +664,7 @@ retry_shape:
     for (int p = 0; p < n_pipes; ++p) CK(cudaStreamWaitEvent(ctx->pipes[p].stream, ctx->pass_begin, 0));
     const bool stats = ctx->stats_enabled;
     uint32_t max_bounce = sc.settings.max_bounce_count;
+    if (sc.settings.integrator == BPT_INTEGRATOR_NORMALS || sc.settings.integrator == BPT_INTEGRATOR_DISTANCES) max_bounce = 1;   // one intersect_scene per sample
     uint32_t batch_index = 0;
 
     for (uint32_t sa = 0; sa < spp; sa += S) {

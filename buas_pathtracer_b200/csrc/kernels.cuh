@@ -394,12 +394,85 @@ BPT_D uint32_t queue_append(uint32_t* counter, bool want) {
     return base + __popc(mask & ((1u << lane) - 1u));
 }
 
+// The reference's single-ray and ground-truth integrators (g_integrators[], integrators.cpp:823-830), one bounce of ONE
+// path:  "Normals" (:544-561) and "Distances" (:563-580) end at their first hit; "Ground Truth Iterative" (:486-542)
+// is the plain path tracer -- Fresnel reflection or uniform-hemisphere diffuse, no NEE, no roulette, one
+// random_unilaterals() per hit.  They use the surface material as is (eta_i = 1, no material stack, no absorption).
+BPT_D void shade_path_simple(const DScene& sc, const DPathState& st, const BatchDesc& b, uint32_t bounce, uint32_t slot,
+                             bool& alive) {
+    const int integrator = sc.settings.integrator;
+    float4 ro4 = st.ray_o[slot], rd4 = st.ray_d[slot], h4 = st.hit[slot];
+    V3 ro = v3(ro4), rd = v3(rd4);
+    HitRecord h;
+    h.t = h4.x; h.prim = __float_as_uint(h4.y); h.tri = __float_as_uint(h4.z); h.v = h4.w; h.w = sc.normals ? st.hit_w[slot] : 0.0f;
+    float4 tp4 = st.throughput[slot];
+    V3 throughput = v3(tp4);
+    V3 total = v3(st.radiance[slot]);
+    if (b.want_records) { float4 pd = st.primary_d[slot]; pd.w = __uint_as_float(__float_as_uint(pd.w) + 1u); st.primary_d[slot] = pd; }
+    alive = false;
+
+    if (h.prim == BPT_HIT_MISS) {
+        if (integrator == BPT_INTEGRATOR_GT_ITERATIVE) total = total + throughput*sample_sky(sc, rd);            // :538
+        else total = sample_sky(sc, rd);                                                                         // :559, :578
+    } else {
+        V3 I, N;
+        uint32_t surface_id;
+        hit_geometry(sc, ro, rd, h, I, N, surface_id);
+        if (integrator == BPT_INTEGRATOR_NORMALS) {
+            total = 0.5f*(v3(1.0f) + N);                                                                         // :557
+        } else if (integrator == BPT_INTEGRATOR_DISTANCES) {
+            total = v3(1.0f - clamp_t(h.t / 15.0f, 0.0f, 1.0f));                                                 // :576
+        } else {
+            MatView m = load_material(sc, surface_id);
+            if (m.flags & BPT_MATERIAL_EMISSIVE) {
+                total = total + throughput*m.emission;                                                           // :505-508
+            } else {
+                uint4 rng = st.rng[slot];
+                next_set(rng);                                                                                   // random_unilaterals :510
+                float rx = unilateral(rng.x);
+                V2 ryz; ryz.x = unilateral(rng.y); ryz.y = unilateral(rng.z);
+                float eta_i = 1.0f, eta_t = m.ior;
+                float ratio = eta_i / eta_t;
+                float cos_i = -dot(rd, N);
+                float cos_t;
+                float reflectance = fresnel_dielectric(cos_i, eta_i, eta_t, ratio, cos_t);
+                V3 next_o, next_d;
+                if (rx < reflectance) {                                                                          // :522-523
+                    V3 refl = reflect(rd, N);
+                    next_o = I + refl*kEps; next_d = refl;
+                } else {                                                                                         // :525-533
+                    V3 albedo = m.albedo;
+                    if (m.flags & BPT_MATERIAL_CHECKERS) {
+                        int checker = (((int)floorf(0.25f*I.x)) ^ ((int)floorf(0.25f*I.z))) & 1;
+                        if (checker) albedo = m.checker;
+                    }
+                    V3 brdf = albedo*(1.0f / kPi);
+                    throughput = throughput*brdf;
+                    V3 R = map_to_hemisphere(N, ryz);
+                    next_o = I + N*kEps; next_d = R;
+                    throughput = throughput*dot(R, N);
+                    throughput = throughput*(2.0f*kPi);
+                }
+                alive = bounce + 1 < sc.settings.max_bounce_count;
+                if (alive) {
+                    st.ray_o[slot] = make_float4(next_o.x, next_o.y, next_o.z, 3.402823466e+38f);
+                    st.ray_d[slot] = make_float4(next_d.x, next_d.y, next_d.z, 0.0f);
+                    st.rng[slot] = rng;
+                    st.throughput[slot] = make_float4(throughput.x, throughput.y, throughput.z, tp4.w);
+                }
+            }
+        }
+    }
+    st.radiance[slot] = make_float4(total.x, total.y, total.z, 0.0f);
+}
+
 // One bounce of advanced_integrator (integrators.cpp:612-818) for ONE path: reads the path's state and the hit of its
 // current ray, accumulates emission / sky, draws the next direction, and reports whether the path continues
 // (its next ray is then in st.ray_o/ray_d) and whether it queued an NEE shadow ray (`sh`).
 BPT_D void shade_path(const DScene& sc, const DPathState& st, const BatchDesc& b, uint32_t bounce, uint32_t slot,
                       bool& alive, bool& want_shadow, DShadowItem& sh) {
     const bpt_settings& set = sc.settings;
+    if (set.integrator != BPT_INTEGRATOR_ADVANCED) { shade_path_simple(sc, st, b, bounce, slot, alive); return; }
     float4 ro4 = st.ray_o[slot], rd4 = st.ray_d[slot], h4 = st.hit[slot];
     V3 ro = v3(ro4), rd = v3(rd4);
     HitRecord h;
