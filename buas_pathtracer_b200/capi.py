@@ -110,7 +110,7 @@ def _fptr(a):
 
 HOST_SCENE_SYMBOLS = [
     "scene_create", "scene_destroy", "add_material", "add_diffuse_material", "add_translucent_material",
-    "add_emissive_material", "add_plane", "add_sphere", "add_box", "create_mesh", "add_mesh", "set_sky",
+    "add_emissive_material", "add_plane", "add_sphere", "add_box", "create_mesh", "add_mesh", "set_sky", "set_ambient_light",
     "set_skydome", "get_camera", "set_camera", "aim_camera", "aim_camera_at", "get_settings", "set_settings",
     "find_integrator", "load_reconstruction_kernel", "get_filter_cache", "set_filter_cache",
     "create_scene_bvh", "get_scene_bvh", "get_mesh_bvh", "get_counts",
@@ -134,6 +134,7 @@ def bind_host_scene(lib, prefix):
         "create_mesh": (C.c_uint32, [vp, C.c_uint32, P(C.c_float), P(C.c_float)]),
         "add_mesh": (C.c_uint32, [vp, C.c_uint32, C.c_uint32, P(M4x4Inv)]),
         "set_sky": (C.c_int, [vp, c_float3, c_float3]),
+        "set_ambient_light": (C.c_int, [vp, c_float3]),
         "set_skydome": (C.c_int, [vp, C.c_uint32, C.c_uint32, P(C.c_float)]),
         "get_camera": (C.c_int, [vp, P(Camera)]),
         "set_camera": (C.c_int, [vp, P(Camera)]),
@@ -245,6 +246,9 @@ class HostScene:
     # -- environment --
     def set_sky(self, top, bot):
         return self.api.set_sky(self.handle, _f3(top), _f3(bot))
+
+    def set_ambient_light(self, rgb):
+        return self.api.set_ambient_light(self.handle, _f3(rgb))
 
     def set_skydome(self, pixels):
         px = np.ascontiguousarray(pixels, dtype=np.float32)

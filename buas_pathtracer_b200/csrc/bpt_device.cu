@@ -203,6 +203,7 @@ void latch_settings(bpt_ctx* ctx, const bpt_scene* scene) {
     ctx->sc.filter_lut_size = scene->filter.cache_size;
     memcpy(ctx->sc.top_sky, scene->top_sky_color, 12);
     memcpy(ctx->sc.bot_sky, scene->bot_sky_color, 12);
+    memcpy(ctx->sc.ambient_light, scene->ambient_light, 12);
 }
 
 } // namespace
@@ -574,13 +575,10 @@ static int render_rows(bpt_ctx* ctx, int32_t x0, int32_t x1, const std::vector<i
     if (seed_mode != BPT_SEED_PER_PIXEL) { set_error("%s: unknown seed mode", who); return BPT_ERR_ARG; }
     if (x0 < 0 || x1 > (int32_t)ctx->film_w || x0 >= x1 || rows.empty() || spp == 0) { set_error("%s: bad rect/spp", who); return BPT_ERR_ARG; }
     for (int32_t y : rows) if (y < 0 || y >= (int32_t)ctx->film_h) { set_error("%s: bad rect/spp (row %d)", who, y); return BPT_ERR_ARG; }
-    {
-        int ig = ctx->sc.settings.integrator;
-        if (ig == BPT_INTEGRATOR_WHITTED || ig == BPT_INTEGRATOR_GT_RECURSIVE) {
-            // the two recursive integrators (integrators.cpp:310-484) are not built; refuse rather than substitute
-            set_error("%s: the \"Whitted\" and \"Ground Truth Recursive\" integrators do not run on the device (SURVEY 8f rank 4)", who);
-            return BPT_ERR_UNSUPPORTED;
-        }
+    const bool recursive = ctx->sc.settings.integrator == BPT_INTEGRATOR_WHITTED || ctx->sc.settings.integrator == BPT_INTEGRATOR_GT_RECURSIVE;
+    if (recursive && ctx->sc.settings.max_bounce_count > BPT_MAX_RECURSION) {
+        set_error("%s: the recursive integrators support max_bounce_count <= %d", who, BPT_MAX_RECURSION);
+        return BPT_ERR_UNSUPPORTED;
     }
     if (ctx->sc.filter_lut_size != 0 && ctx->sc.filter_radius == 0) { set_error("%s: filter LUT with radius 0", who); return BPT_ERR_ARG; }
     CK(cudaSetDevice(ctx->device));
@@ -685,6 +683,17 @@ retry_shape:
             end_span(ctx, s);
             ctx->launches++;
 
+            if (recursive) {
+                // "Whitted" / "Ground Truth Recursive": every sample is evaluated to completion by one launch (recursive.cuh)
+                begin_span(ctx, ST_TRACE, s);
+                uint32_t rg = grid_for(ctx, b.slots, 128, 4);
+                if (sc.settings.integrator == BPT_INTEGRATOR_WHITTED) k_recursive<true ><<<rg, 128, 0, s>>>(sc, pp.st, b, ctx->tail_refill, ctx->d_stats);
+                else                                                  k_recursive<false><<<rg, 128, 0, s>>>(sc, pp.st, b, ctx->tail_refill, ctx->d_stats);
+                debug_sync("k_recursive", 0, s);
+                end_span(ctx, s);
+                ctx->launches++; ctx->trace_launches++;
+                max_bounce = 0;
+            }
             uint32_t* counters = pp.q.counters;
             // Per bounce b:  trace { extension rays of b  +  shadow rays queued by bounce b-1 }  ->  shade b.
             // counters: [0]/[1] = active-queue sizes (ping-pong), [2] = shadow count, [3] = fetch cursor.

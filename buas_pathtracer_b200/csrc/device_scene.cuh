@@ -74,6 +74,7 @@ struct DScene {
     uint32_t air_material;             // == material_count
     uint32_t skydome_w, skydome_h;
     float top_sky[3], bot_sky[3];
+    float ambient_light[3];
 
     bpt_camera   camera;               // latched Scene::camera
     bpt_settings settings;             // latched Scene::settings

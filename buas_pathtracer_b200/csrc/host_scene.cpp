@@ -301,6 +301,11 @@ int bpt_set_sky(bpt_scene* s, const float top[3], const float bot[3]) {
     return BPT_OK;
 }
 
+int bpt_set_ambient_light(bpt_scene* s, const float rgb[3]) {
+    memcpy(s->ambient_light, rgb, 12);
+    return BPT_OK;
+}
+
 int bpt_set_skydome(bpt_scene* s, uint32_t w, uint32_t h, const float* pixels) {
     if (!pixels) { s->skydome.clear(); s->skydome_w = s->skydome_h = 0; return BPT_OK; }
     s->skydome_w = w; s->skydome_h = h;

@@ -69,6 +69,7 @@ struct bpt_scene {
 
     float top_sky_color[3] = {0, 0, 0};
     float bot_sky_color[3] = {0, 0, 0};
+    float ambient_light[3] = {0, 0, 0};
     uint32_t skydome_w = 0, skydome_h = 0;
     bpt::PinnedVec<float> skydome;       // w*h*3
 

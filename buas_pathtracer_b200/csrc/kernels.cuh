@@ -816,6 +816,10 @@ k_tail(DScene sc, DPathState st, BatchDesc b, uint32_t first_bounce, const uint3
     flush_ray_counts(stats, src.n_rays, src.n_shadow);
 }
 
+} // namespace bpt
+#include "recursive.cuh"
+namespace bpt {
+
 // render_tile's tail (raytracer.cpp:469-488) + splat_filter (:187-259): one thread per pixel of the batch walks that
 // pixel's samples, keeps the (2r+1)^2 footprint in registers, and flushes it with vector atomics.
 template <int R>

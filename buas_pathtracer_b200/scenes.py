@@ -158,6 +158,32 @@ def c4_nested_dielectrics(scene, w, h, marbles=24, seed=7):
     scene.create_scene_bvh()
 
 
+def whitted_showcase(scene, w, h):
+    """Test scene for the recursive integrators in the style of the reference's week 1/2 scenes (raytracer.cpp:793-838):
+    checker ground, a metallic rough sphere, a glossy dielectric sphere (reflectance above and below the 0.05 branch),
+    a glass ball with an air bubble (two recursive children per hit), two sphere lights, ambient light set."""
+    _camera(scene, w, h, (0, 5, -16), 50.0, look_at=(0, 3, 0))
+    _advanced(scene, max_bounce_count=6)
+    scene.set_sky((0.6, 0.75, 1.0), (0.95, 0.9, 0.8))
+    scene.set_ambient_light((0.3, 0.35, 0.4))
+    ground = scene.add_diffuse_material((0.8, 0.8, 0.8), 1.0, 0.0, True, (0.15, 0.15, 0.2))
+    red = scene.add_diffuse_material((0.85, 0.2, 0.15), 1.6, 0.0)
+    metal = scene.add_material(albedo=(0.9, 0.75, 0.3), ior=1.4, metallic=0.85, roughness=0.15)
+    glass = scene.add_translucent_material((0.2, 0.05, 0.3), 1.5, 0.02)
+    air = scene.add_translucent_material((0, 0, 0), 1.0)
+    l1 = scene.add_emissive_material((900, 850, 700))
+    l2 = scene.add_emissive_material((200, 300, 500))
+    scene.add_plane(ground, (0, 1, 0), 0.0)
+    scene.add_sphere(red, 2.0, translate((-5.0, 2.0, 2.0)))
+    scene.add_sphere(metal, 2.5, translate((5.0, 2.5, 3.0)))
+    scene.add_sphere(glass, 2.2, translate((0.0, 2.2, -2.0)))
+    scene.add_sphere(air, 0.8, translate((0.3, 2.4, -2.2)))
+    scene.add_box(red, (1.0, 1.0, 1.0), trs((-1.5, 1.0, 6.0), 0.6, 1.0))
+    scene.add_sphere(l1, 0.5, translate((6.0, 14.0, -6.0)))
+    scene.add_sphere(l2, 0.4, translate((-8.0, 9.0, -4.0)))
+    scene.create_scene_bvh()
+
+
 CONFIGS = {
     "c1": dict(build=c1_week3, w=640, h=360, spp=16,
                name="reference built-in sphere scene (week_3_scene) 640x360 16 spp"),

@@ -208,6 +208,8 @@ BPT_API uint32_t bpt_add_mesh  (bpt_scene* s, uint32_t material_id, uint32_t mes
 
 /* Scene::top_sky_color / bot_sky_color / skydome (scene.h:92-96, assets.h:29-37). pixels = w*h*3 floats, copied. */
 BPT_API int bpt_set_sky(bpt_scene* s, const float top[3], const float bot[3]);
+/* Scene::ambient_light (scene.h:102), read by the "Whitted" integrator only (integrators.cpp:371); default 0 */
+BPT_API int bpt_set_ambient_light(bpt_scene* s, const float rgb[3]);
 BPT_API int bpt_set_skydome(bpt_scene* s, uint32_t w, uint32_t h, const float* pixels);
 
 /* Scene::new_camera / new_settings latched as render_all_tiles does (raytracer.cpp:711-720,

@@ -26,6 +26,7 @@ BPT_API uint32_t ref_add_box   (ref_scene* s, uint32_t mat, const float r[3], co
 BPT_API uint32_t ref_create_mesh(ref_scene* s, uint32_t triangle_count, const float* positions, const float* normals);
 BPT_API uint32_t ref_add_mesh  (ref_scene* s, uint32_t mat, uint32_t mesh, const bpt_m4x4inv* xf);
 BPT_API int ref_set_sky(ref_scene* s, const float top[3], const float bot[3]);
+BPT_API int ref_set_ambient_light(ref_scene* s, const float rgb[3]);
 BPT_API int ref_set_skydome(ref_scene* s, uint32_t w, uint32_t h, const float* pixels);
 BPT_API int ref_get_camera(const ref_scene* s, bpt_camera* out);
 BPT_API int ref_set_camera(ref_scene* s, const bpt_camera* c);

@@ -119,6 +119,11 @@ BPT_API int ref_set_sky(ref_scene* s, const float top[3], const float bot[3]) {
     return 0;
 }
 
+BPT_API int ref_set_ambient_light(ref_scene* s, const float rgb[3]) {
+    s->scene.ambient_light = to_v3(rgb);
+    return 0;
+}
+
 BPT_API int ref_set_skydome(ref_scene* s, uint32_t w, uint32_t h, const float* pixels) {
     if (!pixels) { s->scene.skydome = nullptr; return 0; }
     s->skydome.w = w; s->skydome.h = h;
