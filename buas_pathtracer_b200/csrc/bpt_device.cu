@@ -11,6 +11,7 @@
 
 #include "host_scene.h"
 #include "kernels.cuh"
+#include "bvh_device.cuh"
 
 using namespace bpt;
 
@@ -857,6 +858,112 @@ int bpt_resolve_bgra8(bpt_ctx* ctx, const bpt_post_settings* post, const uint8_t
     cudaFree(d_out); cudaFree(d_dither);
     if (e != cudaSuccess) { set_error("bpt_resolve_bgra8: %s", cudaGetErrorString(e)); return BPT_ERR_CUDA; }
     ctx->d2h_bytes += n*sizeof(uint32_t);
+    return BPT_OK;
+}
+
+int bpt_build_mesh_bvh_device(bpt_ctx* ctx, uint32_t n, const float* positions, bpt_bvh_node* nodes_out,
+                              uint32_t node_capacity, uint32_t* node_count, uint32_t* indices_out, float* build_ms) {
+    using namespace bpt::gbvh;
+    static_assert(sizeof(OutNode) == sizeof(bpt_bvh_node), "node layout");
+    if (!ctx || !positions || !nodes_out || !node_count || !indices_out || n == 0) { set_error("bpt_build_mesh_bvh_device: null argument"); return BPT_ERR_ARG; }
+    if (node_capacity < 2ull*n + 2 && node_capacity < 2) { set_error("bpt_build_mesh_bvh_device: node buffer too small"); return BPT_ERR_ARG; }
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    const uint32_t T = 256;
+    auto blocks = [&](uint64_t work) { return (uint32_t)((work + T - 1)/T); };
+    const uint32_t max_level_nodes = (uint32_t)std::max<uint64_t>(4, 2ull*n/5 + 4);
+    const uint32_t tiles = (n + kScanTile - 1)/kScanTile;
+
+    std::vector<void*> owned;
+    auto dalloc = [&](void** p, size_t bytes) -> int { CK(cudaMalloc(p, std::max<size_t>(bytes, 256))); owned.push_back(*p); return BPT_OK; };
+    float* d_pos = nullptr; GEntry* d_e[2] = {nullptr, nullptr}; uint32_t* d_seg[2] = {nullptr, nullptr};
+    uint2 *d_flags = nullptr, *d_scan = nullptr, *d_tiles = nullptr;
+    uint32_t *d_posA = nullptr, *d_posB = nullptr, *d_perm = nullptr, *d_next = nullptr, *d_idx = nullptr;
+    GNode* d_nodes = nullptr; GAcc* d_acc = nullptr; OutNode* d_out = nullptr;
+    int rc = 0;
+    rc |= dalloc((void**)&d_pos, (size_t)n*9*sizeof(float));
+    for (int k = 0; k < 2; ++k) { rc |= dalloc((void**)&d_e[k], (size_t)n*sizeof(GEntry)); rc |= dalloc((void**)&d_seg[k], (size_t)n*4); }
+    rc |= dalloc((void**)&d_flags, (size_t)n*8);
+    rc |= dalloc((void**)&d_scan, ((size_t)n + 1)*8);
+    rc |= dalloc((void**)&d_tiles, (size_t)tiles*8);
+    rc |= dalloc((void**)&d_posA, (size_t)n*4); rc |= dalloc((void**)&d_posB, (size_t)n*4); rc |= dalloc((void**)&d_perm, (size_t)n*4);
+    rc |= dalloc((void**)&d_next, 256); rc |= dalloc((void**)&d_idx, (size_t)n*4);
+    rc |= dalloc((void**)&d_nodes, ((size_t)2*n + 4)*sizeof(GNode));
+    rc |= dalloc((void**)&d_acc, (size_t)max_level_nodes*sizeof(GAcc));
+    rc |= dalloc((void**)&d_out, ((size_t)2*n + 2)*sizeof(OutNode));
+    auto cleanup = [&]() { for (void* p : owned) cudaFree(p); };
+    if (rc) { cleanup(); set_error("bpt_build_mesh_bvh_device: out of device memory"); return BPT_ERR_CUDA; }
+
+    cudaEvent_t ev0, ev1;
+    cudaEventCreate(&ev0); cudaEventCreate(&ev1);
+    cudaError_t err = cudaMemcpyAsync(d_pos, positions, (size_t)n*9*sizeof(float), cudaMemcpyHostToDevice, s);
+    ctx->h2d_bytes += (uint64_t)n*9*sizeof(float);
+    cudaEventRecord(ev0, s);
+    k_make_entries<<<blocks(n), T, 0, s>>>(d_pos, n, d_e[0], d_seg[0]);
+    k_init_root<<<1, 1, 0, s>>>(d_nodes, n);
+    std::vector<std::pair<uint32_t, uint32_t>> levels;      // (first breadth-first id, count)
+    uint32_t lvl_start = 0, lvl_count = 1;
+    int cur = 0;
+    uint64_t launches = 2;
+    while (lvl_count > 0 && err == cudaSuccess) {
+        if (levels.size() >= 512 || lvl_count > max_level_nodes) { err = cudaErrorUnknown; break; }
+        levels.push_back({lvl_start, lvl_count});
+        GNode* lv = d_nodes + lvl_start;
+        uint32_t next_base = lvl_start + lvl_count;
+        cudaMemsetAsync(d_next, 0, 4, s);
+        k_init_acc<<<blocks(lvl_count), T, 0, s>>>(d_acc, lvl_count);
+        k_bounds<<<blocks(n), T, 0, s>>>(d_e[cur], d_seg[cur], n, d_acc);
+        k_decide<<<blocks(lvl_count), T, 0, s>>>(lv, d_acc, lvl_count);
+        k_bin<<<blocks(n), T, 0, s>>>(d_e[cur], d_seg[cur], n, d_acc);
+        k_sah<<<blocks(lvl_count), T, 0, s>>>(lv, d_acc, lvl_count);
+        k_flags<<<blocks(n), T, 0, s>>>(d_e[cur], d_seg[cur], n, d_acc, d_flags, d_perm);
+        k_scan_tiles<<<tiles, kScanBlock, 0, s>>>(d_flags, n, d_scan, d_tiles);
+        k_scan_tile_sums<<<1, 1024, 0, s>>>(d_tiles, tiles, d_scan, n);
+        k_scan_add<<<blocks(n), T, 0, s>>>(d_scan, n, d_tiles);
+        k_scatter<<<blocks(n), T, 0, s>>>(d_seg[cur], n, lv, d_acc, d_flags, d_scan, d_posA, d_posB);
+        k_pair<<<blocks(n), T, 0, s>>>(d_seg[cur], n, lv, d_acc, d_scan, d_posA, d_posB, d_perm);
+        k_split<<<blocks(lvl_count), T, 0, s>>>(lv, d_acc, lvl_count, d_scan, d_posA, d_posB, d_nodes + next_base, next_base, d_next);
+        k_apply<<<blocks(n), T, 0, s>>>(d_e[cur], d_e[cur ^ 1], d_perm, d_seg[cur], d_seg[cur ^ 1], n, lv, d_acc);
+        launches += 13;
+        uint32_t next_count = 0;
+        err = cudaMemcpyAsync(&next_count, d_next, 4, cudaMemcpyDeviceToHost, s);
+        if (err == cudaSuccess) err = cudaStreamSynchronize(s);
+        cur ^= 1;
+        lvl_start = next_base; lvl_count = next_count;
+    }
+    uint32_t total = lvl_start;
+    uint32_t inner_root = 0;
+    if (err == cudaSuccess) {
+        for (size_t l = levels.size(); l-- > 0;) k_inner_count<<<blocks(levels[l].second), T, 0, s>>>(d_nodes, levels[l].first, levels[l].second);
+        for (size_t l = 0; l < levels.size(); ++l) k_rank<<<blocks(levels[l].second), T, 0, s>>>(d_nodes, levels[l].first, levels[l].second);
+        launches += 2*levels.size();
+        GNode root;
+        err = cudaMemcpyAsync(&root, d_nodes, sizeof(GNode), cudaMemcpyDeviceToHost, s);
+        if (err == cudaSuccess) err = cudaStreamSynchronize(s);
+        inner_root = root.inner_count;
+    }
+    uint32_t out_count = 2u + 2u*inner_root;
+    if (err == cudaSuccess && out_count > node_capacity) { cleanup(); cudaEventDestroy(ev0); cudaEventDestroy(ev1); set_error("bpt_build_mesh_bvh_device: node buffer too small (%u nodes)", out_count); return BPT_ERR_ARG; }
+    if (err == cudaSuccess) {
+        cudaMemsetAsync(d_out, 0, (size_t)out_count*sizeof(OutNode), s);
+        k_emit<<<blocks(total), T, 0, s>>>(d_nodes, total, d_out);
+        k_indices<<<blocks(n), T, 0, s>>>(d_e[cur], n, d_idx);
+        launches += 2;
+        cudaEventRecord(ev1, s);
+        err = cudaMemcpyAsync(nodes_out, d_out, (size_t)out_count*sizeof(OutNode), cudaMemcpyDeviceToHost, s);
+        if (err == cudaSuccess) err = cudaMemcpyAsync(indices_out, d_idx, (size_t)n*4, cudaMemcpyDeviceToHost, s);
+        if (err == cudaSuccess) err = cudaStreamSynchronize(s);
+        if (err == cudaSuccess) err = cudaGetLastError();
+        ctx->d2h_bytes += (uint64_t)out_count*sizeof(OutNode) + (uint64_t)n*4;
+    }
+    float ms = 0.0f;
+    if (err == cudaSuccess) cudaEventElapsedTime(&ms, ev0, ev1);
+    cudaEventDestroy(ev0); cudaEventDestroy(ev1);
+    cleanup();
+    ctx->total_launches += launches;
+    if (err != cudaSuccess) { set_error("bpt_build_mesh_bvh_device: %s", cudaGetErrorString(err)); cudaGetLastError(); return BPT_ERR_CUDA; }
+    *node_count = out_count;
+    if (build_ms) *build_ms = ms;
     return BPT_OK;
 }
 

@@ -287,6 +287,34 @@ uint32_t bpt_create_mesh(bpt_scene* s, uint32_t triangle_count, const float* pos
     return (uint32_t)s->meshes.size() - 1;
 }
 
+uint32_t bpt_create_mesh_with_bvh(bpt_scene* s, uint32_t triangle_count, const float* positions, const float* normals,
+                                  const bpt_bvh_node* nodes, uint32_t node_count, const uint32_t* indices) {
+    if (!positions || triangle_count == 0 || !nodes || node_count == 0 || !indices) { set_error("bpt_create_mesh_with_bvh: null argument"); return 0xFFFFFFFFu; }
+    for (uint32_t i = 0; i < triangle_count; ++i)
+        if (indices[i] >= triangle_count) { set_error("bpt_create_mesh_with_bvh: index %u out of range", indices[i]); return 0xFFFFFFFFu; }
+    s->meshes.emplace_back();
+    HostMesh& m = s->meshes.back();
+    m.triangle_count = triangle_count;
+    m.positions.assign(positions, positions + (size_t)triangle_count*9);
+    if (normals) {
+        m.has_normals = true;
+        m.normals.assign(normals, normals + (size_t)triangle_count*9);
+    }
+    m.bvh.nodes.assign(nodes, nodes + node_count);
+    m.bvh.indices.assign(indices, indices + triangle_count);
+    float ext = 0.0f;
+    for (uint32_t i = 0; i < node_count; ++i)
+        for (int k = 0; k < 3; ++k) {
+            float e = fabsf(nodes[i].bv_p[k]) + fabsf(nodes[i].bv_r[k]);
+            if (!(e <= ext)) ext = e;
+        }
+    m.bvh.max_abs_extent = ext;
+    m.leaf_triangles.resize((size_t)triangle_count*9);
+    for (uint32_t i = 0; i < triangle_count; ++i)
+        memcpy(&m.leaf_triangles[(size_t)i*9], &m.positions[(size_t)indices[i]*9], 9*sizeof(float));
+    return (uint32_t)s->meshes.size() - 1;
+}
+
 uint32_t bpt_add_mesh(bpt_scene* s, uint32_t mat, uint32_t mesh, const bpt_m4x4inv* xf) {
     if (mesh >= s->meshes.size()) { set_error("bpt_add_mesh: unknown mesh %u", mesh); return 0xFFFFFFFFu; }
     uint32_t id;

@@ -15,6 +15,7 @@ DEVICE_SYMBOLS = [
     "create", "destroy", "set_sampler_tables", "upload_scene", "update_settings", "film_resize", "film_clear",
     "film_use_external", "film_device_ptr", "download_film", "render_pass", "render_pass_bands", "sync", "trace", "set_sample_records",
     "stats_enable", "get_stats", "get_pass_timing", "set_detailed_timing", "set_tail_threshold", "get_transfer_bytes", "resolve_bgra8",
+    "build_mesh_bvh_device",
 ]
 MISC_SYMBOLS = ["last_error", "version", "make_displaced_icosphere", "make_procedural_skydome"]
 
@@ -93,6 +94,8 @@ def load_library():
     L.bpt_set_detailed_timing.argtypes = [vp, C.c_int]
     L.bpt_set_tail_threshold.restype = C.c_int
     L.bpt_set_tail_threshold.argtypes = [vp, C.c_uint32]
+    L.bpt_build_mesh_bvh_device.restype = C.c_int
+    L.bpt_build_mesh_bvh_device.argtypes = [vp, C.c_uint32, vp, vp, C.c_uint32, P(C.c_uint32), vp, P(C.c_float)]
     L.bpt_get_transfer_bytes.restype = C.c_int
     L.bpt_get_transfer_bytes.argtypes = [vp, P(C.c_uint64), P(C.c_uint64), C.c_int]
     L.bpt_resolve_bgra8.restype = C.c_int
@@ -121,6 +124,21 @@ class Scene(capi.HostScene):
 
     def __init__(self):
         super().__init__(load_library(), "bpt_")
+
+    def create_mesh_with_bvh(self, positions, nodes, indices, normals=None):
+        """bpt_create_mesh with a caller-supplied BVH (e.g. Renderer.build_mesh_bvh) instead of the host build"""
+        pos = np.ascontiguousarray(positions, dtype=np.float32).reshape(-1, 9)
+        nodes = np.ascontiguousarray(nodes, dtype=capi.BVH_NODE_DTYPE)
+        idx = np.ascontiguousarray(indices, dtype=np.uint32)
+        nrm = None if normals is None else np.ascontiguousarray(normals, dtype=np.float32).reshape(-1, 9)
+        f = self.lib.bpt_create_mesh_with_bvh
+        f.restype = C.c_uint32
+        f.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]
+        h = f(self.handle, pos.shape[0], pos.ctypes.data, None if nrm is None else nrm.ctypes.data,
+              nodes.ctypes.data, nodes.shape[0], idx.ctypes.data)
+        if h == 0xFFFFFFFF:
+            raise BptError(self.lib.bpt_last_error().decode())
+        return h
 
 
 def make_displaced_icosphere(level, amplitude=0.08):
@@ -228,6 +246,17 @@ class Renderer:
 
     def set_detailed_timing(self, on=True):
         _check(self.lib.bpt_set_detailed_timing(self.handle, int(on)), "bpt_set_detailed_timing")
+
+    def build_mesh_bvh(self, positions):
+        """create_bvh_for_mesh on the device: (nodes, leaf-order indices, device milliseconds)"""
+        pos = np.ascontiguousarray(positions, dtype=np.float32).reshape(-1, 9)
+        n = pos.shape[0]
+        nodes = np.zeros(2 * n + 2, dtype=capi.BVH_NODE_DTYPE)
+        idx = np.zeros(n, dtype=np.uint32)
+        nc, ms = C.c_uint32(), C.c_float()
+        _check(self.lib.bpt_build_mesh_bvh_device(self.handle, n, pos.ctypes.data, nodes.ctypes.data, nodes.shape[0],
+                                                  C.byref(nc), idx.ctypes.data, C.byref(ms)), "bpt_build_mesh_bvh_device")
+        return nodes[:nc.value].copy(), idx, ms.value
 
     def set_tail_threshold(self, paths):
         _check(self.lib.bpt_set_tail_threshold(self.handle, int(paths)), "bpt_set_tail_threshold")

@@ -240,6 +240,9 @@ BPT_API int bpt_get_scene_bvh(const bpt_scene* s, const bpt_bvh_node** nodes, ui
 BPT_API int bpt_get_mesh_bvh(const bpt_scene* s, uint32_t mesh, const bpt_bvh_node** nodes, uint32_t* node_count,
                              const uint32_t** indices, uint32_t* index_count,
                              const float** leaf_order_triangles /* 9 floats each */);
+/* bpt_create_mesh with a BVH supplied by the caller (e.g. from bpt_build_mesh_bvh_device) instead of the host build. */
+BPT_API uint32_t bpt_create_mesh_with_bvh(bpt_scene* s, uint32_t triangle_count, const float* positions, const float* normals,
+                                          const bpt_bvh_node* nodes, uint32_t node_count, const uint32_t* indices);
 BPT_API int bpt_get_counts(const bpt_scene* s, uint32_t* materials, uint32_t* primitives, uint32_t* planes,
                            uint32_t* lights, uint32_t* meshes);
 
@@ -329,6 +332,13 @@ BPT_API int bpt_set_detailed_timing(bpt_ctx* ctx, int enable);
  * fused launch instead of one wavefront round per bounce (the analogue of a render_tile worker simply looping on,
  * raytracer.cpp:409-494).  0 = always wavefront.  Default 65536. */
 BPT_API int bpt_set_tail_threshold(bpt_ctx* ctx, uint32_t paths);
+/* create_bvh_for_mesh (Raytracer/bvh.cpp:342-391, BVH_SAHBinned) built ON THE DEVICE: same node array (numbering
+ * included) and same leaf-order indices as bpt_create_mesh / the reference produce on the host.  nodes_out needs room for
+ * 2*triangle_count + 2 nodes.  build_ms (nullable) receives the device time of the build (entries resident). */
+BPT_API int bpt_build_mesh_bvh_device(bpt_ctx* ctx, uint32_t triangle_count, const float* positions,
+                                      bpt_bvh_node* nodes_out, uint32_t node_capacity, uint32_t* node_count,
+                                      uint32_t* indices_out, float* build_ms);
+
 /* cumulative bytes this context copied host->device / device->host (scene uploads, rays, film, records) */
 BPT_API int bpt_get_transfer_bytes(bpt_ctx* ctx, uint64_t* h2d, uint64_t* d2h, int reset);
 
