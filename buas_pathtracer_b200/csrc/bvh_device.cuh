@@ -171,20 +171,53 @@ __global__ void k_decide(GNode* nodes, GAcc* acc, uint32_t count) {
     a.state = 1;
 }
 
+// Binning (bvh.cpp:157-166).  Near the root every thread of a block feeds the same node's 16 bins: those blocks
+// accumulate in shared memory and issue one set of global atomics per block (7 per entry became 0.4 per entry; the
+// plain version spent 68 % of a 1.3 M-triangle build in this kernel).  Blocks that straddle nodes use global atomics.
 __global__ void k_bin(const GEntry* __restrict__ e, const uint32_t* __restrict__ seg, uint32_t n, GAcc* acc) {
+    __shared__ uint32_t s_cnt[kBins], s_lo[kBins][3], s_hi[kBins][3];
+    __shared__ uint32_t s_node;
     uint32_t i = blockIdx.x*blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    uint32_t s = seg[i];
-    if (s == kInvalid) return;
-    GAcc& a = acc[s];
-    if (a.state != 1) return;
-    GEntry q = e[i];
-    uint32_t b = float_to_u32_x86(a.k1*(q.p[a.axis] - a.k0));
-    if (b >= (uint32_t)kBins) b = kBins - 1;
-    atomicAdd(&a.bin_count[b], 1u);
-    for (int k = 0; k < 3; ++k) {
-        atomicMin(&a.bin_lo[b][k], enc(q.p[k] - q.r[k]));
-        atomicMax(&a.bin_hi[b][k], enc(q.p[k] + q.r[k]));
+    uint32_t s = i < n ? seg[i] : kInvalid;
+    if (threadIdx.x == 0) s_node = s;
+    if (threadIdx.x < kBins) {
+        s_cnt[threadIdx.x] = 0;
+        for (int k = 0; k < 3; ++k) { s_lo[threadIdx.x][k] = enc(FLT_MAX); s_hi[threadIdx.x][k] = enc(-FLT_MAX); }
+    }
+    __syncthreads();
+    const uint32_t node = s_node;
+    const int uniform = __syncthreads_and(i >= n || s == node) && node != kInvalid;
+    bool active = s != kInvalid && acc[s].state == 1;
+    uint32_t b = 0;
+    GEntry q;
+    if (active) {
+        q = e[i];
+        const GAcc& a = acc[s];
+        b = float_to_u32_x86(a.k1*(q.p[a.axis] - a.k0));
+        if (b >= (uint32_t)kBins) b = kBins - 1;
+    }
+    if (uniform) {
+        if (active) {
+            atomicAdd(&s_cnt[b], 1u);
+            for (int k = 0; k < 3; ++k) {
+                atomicMin(&s_lo[b][k], enc(q.p[k] - q.r[k]));
+                atomicMax(&s_hi[b][k], enc(q.p[k] + q.r[k]));
+            }
+        }
+        __syncthreads();
+        GAcc& a = acc[node];
+        if (threadIdx.x < kBins && s_cnt[threadIdx.x] != 0) {
+            uint32_t t = threadIdx.x;
+            atomicAdd(&a.bin_count[t], s_cnt[t]);
+            for (int k = 0; k < 3; ++k) { atomicMin(&a.bin_lo[t][k], s_lo[t][k]); atomicMax(&a.bin_hi[t][k], s_hi[t][k]); }
+        }
+    } else if (active) {
+        GAcc& a = acc[s];
+        atomicAdd(&a.bin_count[b], 1u);
+        for (int k = 0; k < 3; ++k) {
+            atomicMin(&a.bin_lo[b][k], enc(q.p[k] - q.r[k]));
+            atomicMax(&a.bin_hi[b][k], enc(q.p[k] + q.r[k]));
+        }
     }
 }
 
