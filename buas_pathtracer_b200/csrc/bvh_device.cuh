@@ -119,11 +119,20 @@ __global__ void k_init_acc(GAcc* acc, uint32_t count) {
     a.state = 0; a.swaps = 0; a.split_rel = 0; a.child_local = kInvalid; a.axis = 0; a.k0 = a.k1 = a.split_p = 0.0f;
 }
 
-// compute_bounding_volume (bvh.cpp:6-17) for every node of the level at once
+// compute_bounding_volume (bvh.cpp:6-17) for every node of the level at once.  Warps that lie inside one node reduce
+// with REDUX first; blocks that lie inside one node combine their warps in shared memory and issue 12 global atomics.
 __global__ void k_bounds(const GEntry* __restrict__ e, const uint32_t* __restrict__ seg, uint32_t n, GAcc* acc) {
+    __shared__ uint32_t s_v[12];
+    __shared__ uint32_t s_node;
     uint32_t i = blockIdx.x*blockDim.x + threadIdx.x;
     uint32_t s = i < n ? seg[i] : kInvalid;
+    if (threadIdx.x == 0) s_node = s;
+    if (threadIdx.x < 12) s_v[threadIdx.x] = (threadIdx.x % 6) < 3 ? enc(FLT_MAX) : enc(-FLT_MAX);   // lo,hi,lo,hi triples
+    __syncthreads();
+    const uint32_t node = s_node;
+    const int block_uniform = __syncthreads_and(i >= n || s == node) && node != kInvalid;
     uint32_t v[12];
+    for (int k = 0; k < 12; ++k) v[k] = (k % 6) < 3 ? enc(FLT_MAX) : enc(-FLT_MAX);
     if (s != kInvalid) {
         GEntry q = e[i];
         for (int k = 0; k < 3; ++k) {
@@ -131,7 +140,19 @@ __global__ void k_bounds(const GEntry* __restrict__ e, const uint32_t* __restric
             v[6 + k] = enc(q.p[k]);      v[9 + k] = enc(q.p[k]);
         }
     }
-    // whole warp in one node (the common case near the root): reduce in the warp, one lane does the atomics
+    if (block_uniform) {
+        for (int k = 0; k < 12; ++k) {
+            uint32_t r = (k % 6) < 3 ? __reduce_min_sync(0xFFFFFFFFu, v[k]) : __reduce_max_sync(0xFFFFFFFFu, v[k]);
+            if ((threadIdx.x & 31u) == 0) { if ((k % 6) < 3) atomicMin(&s_v[k], r); else atomicMax(&s_v[k], r); }
+        }
+        __syncthreads();
+        if (threadIdx.x < 12) {
+            uint32_t k = threadIdx.x;
+            uint32_t* dst = k < 3 ? &acc[node].bv_lo[k] : k < 6 ? &acc[node].bv_hi[k - 3] : k < 9 ? &acc[node].cr_lo[k - 6] : &acc[node].cr_hi[k - 9];
+            if ((k % 6) < 3) atomicMin(dst, s_v[k]); else atomicMax(dst, s_v[k]);
+        }
+        return;
+    }
     uint32_t s0 = __shfl_sync(0xFFFFFFFFu, s, 0);
     if (__all_sync(0xFFFFFFFFu, s == s0) && s0 != kInvalid) {
         for (int k = 0; k < 3; ++k) {
