@@ -17,7 +17,9 @@ DEVICE_SYMBOLS = [
     "stats_enable", "get_stats", "get_pass_timing", "set_detailed_timing", "set_tail_threshold", "get_transfer_bytes", "resolve_bgra8",
     "build_mesh_bvh_device",
 ]
-MISC_SYMBOLS = ["last_error", "version", "make_displaced_icosphere", "make_procedural_skydome"]
+MISC_SYMBOLS = ["last_error", "version", "make_displaced_icosphere", "make_procedural_skydome",
+                "parse_obj", "load_obj", "obj_free", "obj_triangle_count", "obj_positions", "obj_normals", "obj_texcoords",
+                "create_mesh_from_obj", "parse_hdr", "load_skydome_hdr"]
 
 
 class BptError(RuntimeError):
@@ -149,6 +151,47 @@ def make_displaced_icosphere(level, amplitude=0.08):
     tris = np.zeros((n, 9), np.float32)
     L.bpt_make_displaced_icosphere(level, amplitude, tris.ctypes.data)
     return tris
+
+
+def parse_obj(text, winding=1, path=None):
+    """bpt_parse_obj / bpt_load_obj: (positions, normals|None, texcoords|None) as (n, 9) float32 arrays; raises BptError"""
+    L = load_library()
+    fp = C.POINTER(C.c_float)
+    for name in ("bpt_parse_obj", "bpt_load_obj"):
+        getattr(L, name).restype = C.c_void_p
+        getattr(L, name).argtypes = [C.c_char_p, C.c_int32]
+    L.bpt_obj_free.argtypes = [C.c_void_p]
+    L.bpt_obj_triangle_count.restype = C.c_uint32
+    L.bpt_obj_triangle_count.argtypes = [C.c_void_p]
+    for name in ("bpt_obj_positions", "bpt_obj_normals", "bpt_obj_texcoords"):
+        getattr(L, name).restype = fp
+        getattr(L, name).argtypes = [C.c_void_p]
+    if path is not None:
+        h = L.bpt_load_obj(path.encode(), winding)
+    else:
+        h = L.bpt_parse_obj(text if isinstance(text, bytes) else text.encode(), winding)
+    if not h:
+        raise BptError(L.bpt_last_error().decode())
+    n = L.bpt_obj_triangle_count(h)
+
+    def grab(f):
+        p = f(h)
+        return np.ctypeslib.as_array(p, shape=(n, 9)).copy() if p else None
+    out = (grab(L.bpt_obj_positions) if n else np.zeros((0, 9), np.float32), grab(L.bpt_obj_normals), grab(L.bpt_obj_texcoords))
+    L.bpt_obj_free(h)
+    return out
+
+
+def parse_hdr(data):
+    """bpt_parse_hdr: (h, w, 3) float32 array in the reference's row order; raises BptError"""
+    L = load_library()
+    L.bpt_parse_hdr.restype = C.c_int
+    L.bpt_parse_hdr.argtypes = [C.c_char_p, C.c_size_t, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.c_void_p]
+    w, h = C.c_uint32(), C.c_uint32()
+    _check(L.bpt_parse_hdr(data, len(data), C.byref(w), C.byref(h), None), "bpt_parse_hdr")
+    px = np.zeros((h.value, w.value, 3), np.float32)
+    _check(L.bpt_parse_hdr(data, len(data), C.byref(w), C.byref(h), px.ctypes.data), "bpt_parse_hdr")
+    return px
 
 
 def make_procedural_skydome(w=2048, h=1024):

@@ -240,6 +240,24 @@ BPT_API int bpt_get_scene_bvh(const bpt_scene* s, const bpt_bvh_node** nodes, ui
 BPT_API int bpt_get_mesh_bvh(const bpt_scene* s, uint32_t mesh, const bpt_bvh_node** nodes, uint32_t* node_count,
                              const uint32_t** indices, uint32_t* index_count,
                              const float** leaf_order_triangles /* 9 floats each */);
+/* ---- asset readers: the reference's parse_obj (Raytracer/assets.cpp:187-400) and parse_hdr (:411-600),
+ * same input -> same triangles / texels, quirks included (see csrc/assets.cpp).  Malformed input that would make the
+ * reference read out of bounds or loop forever returns an error here. */
+typedef struct bpt_obj bpt_obj;
+enum { BPT_WINDING_CLOCKWISE = 0, BPT_WINDING_COUNTER_CLOCKWISE = 1 };        /* MeshWinding, assets.h:74-77 */
+BPT_API bpt_obj* bpt_parse_obj(const char* text, int32_t winding);           /* NUL-terminated text; NULL on error */
+BPT_API bpt_obj* bpt_load_obj(const char* path, int32_t winding);
+BPT_API void bpt_obj_free(bpt_obj* obj);
+BPT_API uint32_t bpt_obj_triangle_count(const bpt_obj* obj);
+BPT_API const float* bpt_obj_positions(const bpt_obj* obj);                  /* 9 floats per triangle */
+BPT_API const float* bpt_obj_normals(const bpt_obj* obj);                    /* 9 floats per triangle, or NULL */
+BPT_API const float* bpt_obj_texcoords(const bpt_obj* obj);                  /* 9 floats per triangle, or NULL */
+BPT_API uint32_t bpt_create_mesh_from_obj(bpt_scene* s, const bpt_obj* obj); /* = bpt_create_mesh(positions, normals) */
+/* Radiance .hdr (32-bit_rle_rgbe): pixels == NULL only reports the size; otherwise w*h*3 floats, row order as the
+ * reference stores them (Image_V3, assets.h:29-32). */
+BPT_API int bpt_parse_hdr(const char* data, size_t size, uint32_t* w, uint32_t* h, float* pixels);
+BPT_API int bpt_load_skydome_hdr(bpt_scene* s, const char* path);            /* parse + bpt_set_skydome */
+
 /* bpt_create_mesh with a BVH supplied by the caller (e.g. from bpt_build_mesh_bvh_device) instead of the host build. */
 BPT_API uint32_t bpt_create_mesh_with_bvh(bpt_scene* s, uint32_t triangle_count, const float* positions, const float* normals,
                                           const bpt_bvh_node* nodes, uint32_t node_count, const uint32_t* indices);

@@ -73,6 +73,11 @@ BPT_API int ref_render_parity(ref_scene* s, float* film, uint32_t w, uint32_t h,
 BPT_API int ref_render_threaded(ref_scene* s, uint32_t w, uint32_t h, uint32_t spp, uint32_t threads,
                                 float* film, double* seconds, bpt_stats* stats);
 
+/* The reference's own parse_obj / parse_hdr (assets.cpp:187-400, :423-600).  Two-call pattern: NULL outputs = report sizes. */
+BPT_API int ref_parse_obj(const char* text, int winding, uint32_t* triangle_count, int* has_normals, int* has_texcoords,
+                          float* positions, float* normals, float* texcoords);
+BPT_API int ref_parse_hdr(const char* data, size_t size, uint32_t* w, uint32_t* h, float* pixels);
+
 /* Known-answer helpers straight from the reference's static functions (for device-math unit parity). */
 BPT_API void ref_kat_cosine_hemisphere(const float n[3], const float u[2], float out[3]);   /* integrators.cpp:107-119 */
 BPT_API void ref_kat_hemisphere(const float n[3], const float u[2], float out[3]);          /* integrators.cpp:93-105 */

@@ -127,3 +127,34 @@ def sampler_tables():
 
 def sizeof(name):
     return lib().ref_sizeof(name.encode())
+
+
+def parse_obj(text, winding=1):
+    """the reference's parse_obj (assets.cpp:187-400): (positions, normals|None, texcoords|None) as (n, 9) arrays, or None on a parse error"""
+    L = lib()
+    L.ref_parse_obj.restype = C.c_int
+    L.ref_parse_obj.argtypes = [C.c_char_p, C.c_int, C.POINTER(C.c_uint32), C.POINTER(C.c_int), C.POINTER(C.c_int),
+                                C.c_void_p, C.c_void_p, C.c_void_p]
+    raw = text if isinstance(text, bytes) else text.encode()
+    n, hn, ht = C.c_uint32(), C.c_int(), C.c_int()
+    if L.ref_parse_obj(raw, winding, C.byref(n), C.byref(hn), C.byref(ht), None, None, None) != 0:
+        return None
+    pos = np.zeros((n.value, 9), np.float32)
+    nrm = np.zeros((n.value, 9), np.float32) if hn.value else None
+    tex = np.zeros((n.value, 9), np.float32) if ht.value else None
+    L.ref_parse_obj(raw, winding, C.byref(n), C.byref(hn), C.byref(ht), pos.ctypes.data,
+                    nrm.ctypes.data if nrm is not None else None, tex.ctypes.data if tex is not None else None)
+    return pos, nrm, tex
+
+
+def parse_hdr(data):
+    """the reference's parse_hdr (assets.cpp:423-600): (h, w, 3) float32 array in the reference's row order, or None"""
+    L = lib()
+    L.ref_parse_hdr.restype = C.c_int
+    L.ref_parse_hdr.argtypes = [C.c_char_p, C.c_size_t, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.c_void_p]
+    w, h = C.c_uint32(), C.c_uint32()
+    if L.ref_parse_hdr(data, len(data), C.byref(w), C.byref(h), None) != 0:
+        return None
+    px = np.zeros((h.value, w.value, 3), np.float32)
+    L.ref_parse_hdr(data, len(data), C.byref(w), C.byref(h), px.ctypes.data)
+    return px

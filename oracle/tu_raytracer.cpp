@@ -353,3 +353,47 @@ BPT_API int ref_render_threaded(ref_scene* s, uint32_t w, uint32_t h, uint32_t s
 }
 
 } // extern "C"
+
+// ---- the reference's asset parsers (assets.cpp, compiled unmodified into assets.o) ---------------------------------
+#include <sys/mman.h>
+static void release_arena(Arena* a) { if (a->base) munmap(a->base, a->capacity); delete a; }
+BPT_API int ref_parse_obj(const char* text, int winding, uint32_t* triangle_count, int* has_normals, int* has_texcoords,
+                          float* positions, float* normals, float* texcoords) {
+    ensure_platform();
+    Arena* arena = new Arena(); memset(arena, 0, sizeof(*arena));
+    Arena* temp = new Arena(); memset(temp, 0, sizeof(*temp));
+    (void)push_size(arena, 64); (void)push_size(temp, 64);     // Arena capacity is set lazily on first push (memory_arena.cpp:6-9)
+    size_t len = strlen(text);
+    char* input = (char*)malloc(len + 1);
+    memcpy(input, text, len + 1);
+    Mesh mesh;
+    b32 ok = parse_obj(arena, temp, input, &mesh, winding == 0 ? MeshWinding_Clockwise : MeshWinding_CounterClockwise);
+    free(input);
+    if (!ok) { release_arena(arena); release_arena(temp); return -1; }
+    *triangle_count = mesh.triangle_count;
+    *has_normals = mesh.has_normals ? 1 : 0;
+    *has_texcoords = mesh.has_texture_coordinates ? 1 : 0;
+    if (positions) memcpy(positions, mesh.triangles, (size_t)mesh.triangle_count*sizeof(Triangle));
+    if (normals && mesh.has_normals) memcpy(normals, get_normals(&mesh), (size_t)mesh.triangle_count*sizeof(Triangle));
+    if (texcoords && mesh.has_texture_coordinates) memcpy(texcoords, get_texture_coordinates(&mesh), (size_t)mesh.triangle_count*sizeof(Triangle));
+    release_arena(arena); release_arena(temp);
+    return 0;
+}
+
+BPT_API int ref_parse_hdr(const char* data, size_t size, uint32_t* w, uint32_t* h, float* pixels) {
+    ensure_platform();
+    Arena* arena = new Arena(); memset(arena, 0, sizeof(*arena));
+    Arena* temp = new Arena(); memset(temp, 0, sizeof(*temp));
+    (void)push_size(arena, 64); (void)push_size(temp, 64);
+    char* input = (char*)malloc(size + 1);
+    memcpy(input, data, size);
+    input[size] = 0;
+    Image_V3 image;
+    b32 ok = parse_hdr(arena, temp, input, &image);
+    free(input);
+    if (!ok) { release_arena(arena); release_arena(temp); return -1; }
+    *w = image.w; *h = image.h;
+    if (pixels) memcpy(pixels, image.pixels, (size_t)image.w*image.h*sizeof(V3));
+    release_arena(arena); release_arena(temp);
+    return 0;
+}
