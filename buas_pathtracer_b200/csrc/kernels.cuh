@@ -394,12 +394,14 @@ BPT_D uint32_t queue_append(uint32_t* counter, bool want) {
     return base + __popc(mask & ((1u << lane) - 1u));
 }
 
+BPT_D uint32_t direction_octant(V3 d) { return (d.x < 0.0f ? 1u : 0u) | (d.y < 0.0f ? 2u : 0u) | (d.z < 0.0f ? 4u : 0u); }
+
 // The reference's single-ray and ground-truth integrators (g_integrators[], integrators.cpp:823-830), one bounce of ONE
 // path:  "Normals" (:544-561) and "Distances" (:563-580) end at their first hit; "Ground Truth Iterative" (:486-542)
 // is the plain path tracer -- Fresnel reflection or uniform-hemisphere diffuse, no NEE, no roulette, one
 // random_unilaterals() per hit.  They use the surface material as is (eta_i = 1, no material stack, no absorption).
 BPT_D void shade_path_simple(const DScene& sc, const DPathState& st, const BatchDesc& b, uint32_t bounce, uint32_t slot,
-                             bool& alive) {
+                             bool& alive, uint32_t& octant) {
     const int integrator = sc.settings.integrator;
     float4 ro4 = st.ray_o[slot], rd4 = st.ray_d[slot], h4 = st.hit[slot];
     V3 ro = v3(ro4), rd = v3(rd4);
@@ -459,6 +461,7 @@ BPT_D void shade_path_simple(const DScene& sc, const DPathState& st, const Batch
                     st.ray_d[slot] = make_float4(next_d.x, next_d.y, next_d.z, 0.0f);
                     st.rng[slot] = rng;
                     st.throughput[slot] = make_float4(throughput.x, throughput.y, throughput.z, tp4.w);
+                    octant = direction_octant(next_d);
                 }
             }
         }
@@ -470,9 +473,9 @@ BPT_D void shade_path_simple(const DScene& sc, const DPathState& st, const Batch
 // current ray, accumulates emission / sky, draws the next direction, and reports whether the path continues
 // (its next ray is then in st.ray_o/ray_d) and whether it queued an NEE shadow ray (`sh`).
 BPT_D void shade_path(const DScene& sc, const DPathState& st, const BatchDesc& b, uint32_t bounce, uint32_t slot,
-                      bool& alive, bool& want_shadow, DShadowItem& sh) {
+                      bool& alive, bool& want_shadow, DShadowItem& sh, uint32_t& octant) {
     const bpt_settings& set = sc.settings;
-    if (set.integrator != BPT_INTEGRATOR_ADVANCED) { shade_path_simple(sc, st, b, bounce, slot, alive); return; }
+    if (set.integrator != BPT_INTEGRATOR_ADVANCED) { shade_path_simple(sc, st, b, bounce, slot, alive, octant); return; }
     float4 ro4 = st.ray_o[slot], rd4 = st.ray_d[slot], h4 = st.hit[slot];
     V3 ro = v3(ro4), rd = v3(rd4);
     HitRecord h;
@@ -689,6 +692,7 @@ BPT_D void shade_path(const DScene& sc, const DPathState& st, const BatchDesc& b
                 st.prev_n[slot] = make_float4(N.x, N.y, N.z, __uint_as_float(is_specular ? 1u : 0u));
                 st.mstack_at[slot] = (uint8_t)stack_at;
                 st.throughput[slot] = make_float4(throughput.x, throughput.y, throughput.z, tp4.w);
+                octant = direction_octant(next_d);
             }
         }
     }
@@ -697,37 +701,67 @@ BPT_D void shade_path(const DScene& sc, const DPathState& st, const BatchDesc& b
 }
 
 // One bounce for every active path of the batch (wavefront form of the loop at integrators.cpp:612-818).
-#ifndef BPT_SHADE_MIN_CTAS
-#define BPT_SHADE_MIN_CTAS 8      // 64 registers: measured 14.7 ms vs 18.6 ms at 4 CTAs/128 registers on C2 (latency-bound on path state)
+// Survivors are appended to the next bounce's queue GROUPED BY THE OCTANT OF THEIR NEW DIRECTION: a block sorts its (up
+// to 512) survivors by octant in shared memory and appends them with one atomic.  Neighbouring queue entries already
+// start from neighbouring surface points (the queue follows pixel order); with equal direction signs they also take the
+// same near/far decisions at every node, so the lanes of a traversal warp stay in the same phase for longer.  The order
+// of the queue does not enter any per-path result.
+#ifndef BPT_SHADE_THREADS
+#define BPT_SHADE_THREADS 512
 #endif
-__global__ void __launch_bounds__(128, BPT_SHADE_MIN_CTAS)
+#ifndef BPT_SHADE_MIN_CTAS
+#define BPT_SHADE_MIN_CTAS 2      // x 512 threads = 64 registers: measured 14.7 ms vs 18.6 ms at 128 registers on C2 (latency-bound on path state)
+#endif
+#ifndef BPT_SHADE_SORT
+#define BPT_SHADE_SORT 1
+#endif
+__global__ void __launch_bounds__(BPT_SHADE_THREADS, BPT_SHADE_MIN_CTAS)
 k_shade(DScene sc, DPathState st, BatchDesc b, uint32_t bounce,
         const uint32_t* __restrict__ in_queue, const uint32_t* __restrict__ n_ptr, uint32_t n_fixed,
         uint32_t* __restrict__ out_queue, uint32_t* out_count,
         DShadowItem* __restrict__ shadow_items, uint32_t* shadow_count, DStats* stats) {
+    __shared__ uint32_t s_count[8], s_start[8], s_base;
+    __shared__ uint32_t s_slots[BPT_SHADE_THREADS];
     uint32_t n = n_ptr ? *n_ptr : n_fixed;
     uint32_t n_rays = 0, n_shadow = 0;
-    uint32_t stride = gridDim.x*blockDim.x;
-    uint32_t base = blockIdx.x*blockDim.x + threadIdx.x;
 
-    for (uint32_t i0 = base - (threadIdx.x & 31); i0 < n; i0 += stride) {
-        uint32_t i = i0 + (threadIdx.x & 31);
+    for (uint32_t blk0 = blockIdx.x*blockDim.x; blk0 < n; blk0 += gridDim.x*blockDim.x) {
+        uint32_t i = blk0 + threadIdx.x;
         bool alive = false;          // path continues to the next bounce
         bool want_shadow = false;
-        uint32_t slot = 0;
+        uint32_t slot = 0, octant = 0;
         DShadowItem sh;
+        if (threadIdx.x < 8) s_count[threadIdx.x] = 0;
+        __syncthreads();
 
         if (i < n) {
             slot = in_queue ? in_queue[i] : i;
-            shade_path(sc, st, b, bounce, slot, alive, want_shadow, sh);
+            shade_path(sc, st, b, bounce, slot, alive, want_shadow, sh, octant);
         }
+#if !BPT_SHADE_SORT
+        octant = 0;
+#endif
+        // block-local counting sort of the survivors by octant (rank within the octant from a shared-memory atomic)
+        uint32_t rank = 0;
+        if (alive) rank = atomicAdd(&s_count[octant], 1u);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            uint32_t run = 0;
+            for (int k = 0; k < 8; ++k) { s_start[k] = run; run += s_count[k]; }
+            s_base = run ? atomicAdd(out_count, run) : 0u;
+            s_count[0] = run;                                    // total survivors of this round
+        }
+        __syncthreads();
+        if (alive) s_slots[s_start[octant] + rank] = slot;
+        __syncthreads();
+        uint32_t total = s_count[0];
+        if (threadIdx.x < total) out_queue[s_base + threadIdx.x] = s_slots[threadIdx.x];
 
-        uint32_t qi = queue_append(out_count, alive);
-        if (alive) out_queue[qi] = slot;
         uint32_t si = queue_append(shadow_count, want_shadow);
         if (want_shadow) shadow_items[si] = sh;
         n_rays += (i < n ? 1u : 0u) + (want_shadow ? 1u : 0u);
         n_shadow += want_shadow ? 1u : 0u;
+        __syncthreads();
     }
     flush_ray_counts(stats, n_rays, n_shadow);
 }
@@ -754,7 +788,8 @@ struct TailSrc {
     BPT_D bool next(V3& o, V3& d, float& max_t, uint32_t& ignored, bool& occ) {
         if (!has_shadow && !has_closest) {
             bool cont = false, want_shadow = false;
-            shade_path(*sc, st, *b, bounce, slot, cont, want_shadow, sh);
+            uint32_t octant_unused = 0;
+            shade_path(*sc, st, *b, bounce, slot, cont, want_shadow, sh, octant_unused);
             n_rays += 1u + (want_shadow ? 1u : 0u);
             n_shadow += want_shadow ? 1u : 0u;
             ++bounce;
