@@ -1,7 +1,9 @@
 // Headless driver: what is left of SDL_main (Raytracer/raytracer.cpp:1560-2390) once the Win32/SDL/microui shell is
 // removed -- build a scene, run progressive passes through the C ABI, "Take picture" (resolve + write_bitmap).
 //
-//   bpt_headless [--scene week3|icosphere] [--w W --h H] [--spp N] [--passes P] [--level L] [--device D] [--out file.bmp]
+//   bpt_headless --tables sampler_tables.bin [--scene week3|icosphere|obj] [--obj file.obj [--cw]] [--hdr sky.hdr]
+//                [--integrator "Whitted"|...] [--filter "Gaussian 3"|...] [--gpu-bvh] [--w W --h H] [--spp N] [--passes P]
+//                [--level L] [--device D] [--out file.bmp]
 //
 // It only speaks include/bpt.h (plain C), exactly like a binding inside the reference would.
 #include <stdio.h>
@@ -84,10 +86,56 @@ static void build_icosphere(bpt_scene* s, uint32_t w, uint32_t h, uint32_t level
     bpt_add_sphere(s, light, 0.5f, &lt);
 }
 
+// a mesh from an .obj file (parse_obj, assets.cpp:187-400) on the icosphere scene's stage, scaled into a 7-unit box
+static int build_obj_scene(bpt_scene* s, bpt_ctx* ctx, uint32_t w, uint32_t h, const char* path, int winding, bool gpu_bvh) {
+    bpt_obj* obj = bpt_load_obj(path, winding);
+    if (!obj) { fprintf(stderr, "%s\n", bpt_last_error()); return 1; }
+    uint32_t n = bpt_obj_triangle_count(obj);
+    if (!n) { fprintf(stderr, "%s: no triangles\n", path); return 1; }
+    const float* pos = bpt_obj_positions(obj);
+    float lo[3] = {1e30f, 1e30f, 1e30f}, hi[3] = {-1e30f, -1e30f, -1e30f};
+    for (size_t i = 0; i < (size_t)n*3; ++i)
+        for (int k = 0; k < 3; ++k) { float v = pos[i*3 + k]; if (v < lo[k]) lo[k] = v; if (v > hi[k]) hi[k] = v; }
+    float ext = hi[0] - lo[0];
+    for (int k = 1; k < 3; ++k) if (hi[k] - lo[k] > ext) ext = hi[k] - lo[k];
+    float scale = ext > 0 ? 7.0f/ext : 1.0f;
+    set_camera(s, w, h, 0, 4.5f, -11, 50.0f);
+    const float at[3] = {0, 3.5f, 0};
+    bpt_aim_camera_at(s, at);
+    bpt_camera cam; bpt_get_camera(s, &cam); cam.focus_distance = 1.0f; bpt_set_camera(s, &cam);
+    use_advanced_integrator(s);
+    const float sky[3] = {0.45f, 0.6f, 0.9f};
+    bpt_set_sky(s, sky, sky);
+    const float g0[3] = {0.8f, 0.8f, 0.8f}, g1[3] = {0.25f, 0.25f, 0.25f}, clay[3] = {0.85f, 0.55f, 0.35f}, grey[3] = {0.1f, 0.1f, 0.1f}, e[3] = {4000, 3800, 3500};
+    uint32_t ground = bpt_add_diffuse_material(s, g0, 1.0f, 0.0f, 1, g1);
+    uint32_t mat = bpt_add_diffuse_material(s, clay, 1.0f, 0.0f, 0, grey);
+    uint32_t light = bpt_add_emissive_material(s, e);
+    const float up[3] = {0, 1, 0};
+    bpt_add_plane(s, ground, up, 0.0f);
+    uint32_t mesh;
+    if (gpu_bvh) {      // create_bvh_for_mesh on the device, same arrays as the host build
+        std::vector<bpt_bvh_node> nodes((size_t)2*n + 2);
+        std::vector<uint32_t> order(n);
+        uint32_t node_count = 0; float ms = 0;
+        if (bpt_build_mesh_bvh_device(ctx, n, pos, nodes.data(), (uint32_t)nodes.size(), &node_count, order.data(), &ms) != BPT_OK) { fprintf(stderr, "%s\n", bpt_last_error()); return 1; }
+        printf("device BVH build: %u triangles -> %u nodes in %.2f ms\n", n, node_count, ms);
+        mesh = bpt_create_mesh_with_bvh(s, n, pos, bpt_obj_normals(obj), nodes.data(), node_count, order.data());
+    } else {
+        mesh = bpt_create_mesh_from_obj(s, obj);
+    }
+    bpt_m4x4inv xf = translate(-0.5f*(lo[0] + hi[0])*scale, 0.05f - lo[1]*scale, -0.5f*(lo[2] + hi[2])*scale, scale), lt = translate(9, 14, -9);
+    bpt_add_mesh(s, mat, mesh, &xf);
+    bpt_add_sphere(s, light, 0.5f, &lt);
+    bpt_obj_free(obj);
+    return 0;
+}
+
 #define CHECK(call) do { int rc_ = (call); if (rc_ != BPT_OK) { fprintf(stderr, "%s failed (%d): %s\n", #call, rc_, bpt_last_error()); return 1; } } while (0)
 
 int main(int argc, char** argv) {
     const char* scene_name = "week3"; const char* out = "render.bmp"; const char* tables = nullptr;
+    const char* obj_path = nullptr; const char* hdr_path = nullptr; const char* integrator = nullptr; const char* filter = nullptr;
+    int winding = BPT_WINDING_COUNTER_CLOCKWISE; bool gpu_bvh = false;
     uint32_t w = 640, h = 360, spp = 16, passes = 1, level = 6; int device = 0;
     for (int i = 1; i < argc; ++i) {
         auto next = [&]() -> const char* { return i + 1 < argc ? argv[++i] : ""; };
@@ -100,6 +148,12 @@ int main(int argc, char** argv) {
         else if (!strcmp(argv[i], "--device")) device = atoi(next());
         else if (!strcmp(argv[i], "--out")) out = next();
         else if (!strcmp(argv[i], "--tables")) tables = next();
+        else if (!strcmp(argv[i], "--obj")) { obj_path = next(); scene_name = "obj"; }
+        else if (!strcmp(argv[i], "--cw")) winding = BPT_WINDING_CLOCKWISE;
+        else if (!strcmp(argv[i], "--hdr")) hdr_path = next();
+        else if (!strcmp(argv[i], "--integrator")) integrator = next();
+        else if (!strcmp(argv[i], "--filter")) filter = next();
+        else if (!strcmp(argv[i], "--gpu-bvh")) gpu_bvh = true;
         else { fprintf(stderr, "unknown argument %s\n", argv[i]); return 2; }
     }
     if (!tables) { fprintf(stderr, "--tables <sampler_tables.bin> is required (the sampler lookup tables, see INTEGRATION.md)\n"); return 2; }
@@ -108,16 +162,23 @@ int main(int argc, char** argv) {
     if (!tf || fread(blob.data(), 1, blob.size(), tf) != blob.size()) { fprintf(stderr, "cannot read %s\n", tables); return 2; }
     fclose(tf);
 
-    bpt_scene* scene = bpt_scene_create();
-    if (!strcmp(scene_name, "week3")) build_week3(scene, w, h);
-    else if (!strcmp(scene_name, "icosphere")) build_icosphere(scene, w, h, level);
-    else { fprintf(stderr, "unknown scene %s\n", scene_name); return 2; }
-    auto t0 = std::chrono::steady_clock::now();
-    CHECK(bpt_create_scene_bvh(scene));
-    printf("BVH Construction took: %fs\n", std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count());
-
     bpt_ctx* ctx = nullptr;
     CHECK(bpt_create(device, &ctx));                       // fails when there is no GPU: no CPU fallback
+    bpt_scene* scene = bpt_scene_create();
+    auto t0 = std::chrono::steady_clock::now();
+    if (!strcmp(scene_name, "week3")) build_week3(scene, w, h);
+    else if (!strcmp(scene_name, "icosphere")) build_icosphere(scene, w, h, level);
+    else if (!strcmp(scene_name, "obj") && obj_path) { if (build_obj_scene(scene, ctx, w, h, obj_path, winding, gpu_bvh)) return 1; }
+    else { fprintf(stderr, "unknown scene %s\n", scene_name); return 2; }
+    if (hdr_path) CHECK(bpt_load_skydome_hdr(scene, hdr_path));
+    if (integrator) {
+        int32_t id = bpt_find_integrator(integrator);     // unknown names select the default, like find_integrator (integrators.cpp:832-838)
+        bpt_settings st; bpt_get_settings(scene, &st); st.integrator = id; bpt_set_settings(scene, &st);
+    }
+    if (filter) bpt_load_reconstruction_kernel(scene, filter);   // unknown names select Box (reconstruction_filters.cpp:112)
+    CHECK(bpt_create_scene_bvh(scene));
+    printf("Scene + BVH construction took: %fs\n", std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count());
+
     CHECK(bpt_set_sampler_tables(ctx, blob.data(), blob.data() + 16384, blob.data() + 81920, blob.data() + 212992));
     CHECK(bpt_upload_scene(ctx, scene));
     CHECK(bpt_film_resize(ctx, w, h));
