@@ -695,6 +695,7 @@ retry_shape:
                 ctx->launches++; ctx->trace_launches++;
                 max_bounce = 0;
             }
+            if (max_bounce == 0 && !recursive) CK(cudaMemsetAsync(pp.st.radiance, 0, (size_t)b.slots*sizeof(float4), s));   // no bounce ever writes it (k_raygen leaves it to the first shade)
             uint32_t* counters = pp.q.counters;
             // Per bounce b:  trace { extension rays of b  +  shadow rays queued by bounce b-1 }  ->  shade b.
             // counters: [0]/[1] = active-queue sizes (ping-pong), [2] = shadow count, [3] = fetch cursor.

@@ -254,14 +254,16 @@ k_raygen(DScene sc, DPathState st, BatchDesc b) {
         st.ray_o[slot] = make_float4(ray_o.x, ray_o.y, ray_o.z, 3.402823466e+38f);    // make_ray's FLT_MAX far clip
         st.ray_d[slot] = make_float4(ray_d.x, ray_d.y, ray_d.z, 0.0f);
         st.throughput[slot] = make_float4(1.0f, 1.0f, 1.0f, vignette);
-        st.radiance[slot] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        // radiance (= 0), prev_n (= none, "specular") and material_stack_at (= 0) are what IntegratorState starts with
+        // (integrators.cpp:587-600): the first bounce's shading knows them, so they are not written here nor read there
+        // (49 of 139 bytes per sample; raygen and the first shade are HBM-bound)
         st.rng[slot] = rng;
-        st.prev_n[slot] = make_float4(0.0f, 0.0f, 0.0f, __uint_as_float(1u));          // is_specular_bounce = true
         st.jitter[slot] = make_float2(jx, jy);
-        st.mstack_at[slot] = 0;
         st.mstack[slot] = (uint16_t)sc.air_material;                                    // material_stack[0] = &air
-        st.primary_d[slot] = make_float4(ray_d.x, ray_d.y, ray_d.z, 0.0f);
-        if (b.want_records) st.primary_o[slot] = make_float4(ray_o.x, ray_o.y, ray_o.z, 0.0f);
+        if (b.want_records) {
+            st.primary_d[slot] = make_float4(ray_d.x, ray_d.y, ray_d.z, 0.0f);
+            st.primary_o[slot] = make_float4(ray_o.x, ray_o.y, ray_o.z, 0.0f);
+        }
     }
 }
 
@@ -409,7 +411,7 @@ BPT_D void shade_path_simple(const DScene& sc, const DPathState& st, const Batch
     h.t = h4.x; h.prim = __float_as_uint(h4.y); h.tri = __float_as_uint(h4.z); h.v = h4.w; h.w = sc.normals ? st.hit_w[slot] : 0.0f;
     float4 tp4 = st.throughput[slot];
     V3 throughput = v3(tp4);
-    V3 total = v3(st.radiance[slot]);
+    V3 total = bounce == 0 ? v3(0.0f) : v3(st.radiance[slot]);
     if (b.want_records) { float4 pd = st.primary_d[slot]; pd.w = __uint_as_float(__float_as_uint(pd.w) + 1u); st.primary_d[slot] = pd; }
     alive = false;
 
@@ -482,8 +484,8 @@ BPT_D void shade_path(const DScene& sc, const DPathState& st, const BatchDesc& b
     h.t = h4.x; h.prim = __float_as_uint(h4.y); h.tri = __float_as_uint(h4.z); h.v = h4.w; h.w = sc.normals ? st.hit_w[slot] : 0.0f;
     float4 tp4 = st.throughput[slot];
     V3 throughput = v3(tp4);
-    float4 rad4 = st.radiance[slot];
-    V3 total = v3(rad4);
+    const bool first = bounce == 0;                       // state the ray generation did not write (see k_raygen)
+    V3 total = first ? v3(0.0f) : v3(st.radiance[slot]);
     float4 pd = make_float4(0, 0, 0, 0);
     if (b.want_records) pd = st.primary_d[slot];
     uint32_t ray_count = __float_as_uint(pd.w) + 1u;      // this bounce's intersect_scene call
@@ -495,10 +497,10 @@ BPT_D void shade_path(const DScene& sc, const DPathState& st, const BatchDesc& b
     } else {
         SamplerCtx sm = make_sampler(sc, b, slot);
         uint4 rng = st.rng[slot];
-        float4 pn4 = st.prev_n[slot];
+        float4 pn4 = first ? make_float4(0.0f, 0.0f, 0.0f, __uint_as_float(1u)) : st.prev_n[slot];   // is_specular_bounce starts true
         V3 prev_N = v3(pn4);
         bool is_specular = (__float_as_uint(pn4.w) & 1u) != 0;
-        int stack_at = st.mstack_at[slot];
+        int stack_at = first ? 0 : (int)st.mstack_at[slot];
 
         V3 I, N;
         uint32_t surface_id;
@@ -696,7 +698,7 @@ BPT_D void shade_path(const DScene& sc, const DPathState& st, const BatchDesc& b
             }
         }
     }
-    if (total_changed) st.radiance[slot] = make_float4(total.x, total.y, total.z, 0.0f);
+    if (total_changed || first) st.radiance[slot] = make_float4(total.x, total.y, total.z, 0.0f);
     if (b.want_records) { pd.w = __uint_as_float(ray_count); st.primary_d[slot] = pd; }
 }
 
