@@ -333,7 +333,7 @@ def main():
                 "stage_ms_per_step": {"raygen": raygen_ms, "trace_closest_merged_tail": trace_ms, "shade": shade_ms,
                                       "trace_shadow": shadow_ms, "splat": splat_ms}}
     traffic_file = os.path.join(ROOT, "profiles", "trace_dram_bytes.json")
-    if os.path.exists(traffic_file):
+    if os.path.exists(traffic_file) and args.config == "c2" and world == 1:     # measured for exactly this workload
         tf = json.load(open(traffic_file))
         roofline["traffic"] = tf.get("dram_bytes_per_launch")
         roofline["traffic_source"] = tf.get("source")
