@@ -54,6 +54,7 @@ class BvhNode(C.Structure):
                 ("count", C.c_uint16), ("split_axis", C.c_uint16)]
 
 
+BVH_MIDPOINT_SPLIT, BVH_SAH_BINNED, BVH_SAH_FULL = 0, 1, 2      # BVHConstructionMethod (bvh.h:7-11)
 BVH_NODE_DTYPE = np.dtype([("bv_p", np.float32, 3), ("bv_r", np.float32, 3), ("left_first", np.uint32),
                            ("count", np.uint16), ("split_axis", np.uint16)])
 assert BVH_NODE_DTYPE.itemsize == 32 and C.sizeof(BvhNode) == 32
@@ -110,7 +111,7 @@ def _fptr(a):
 
 HOST_SCENE_SYMBOLS = [
     "scene_create", "scene_destroy", "add_material", "add_diffuse_material", "add_translucent_material",
-    "add_emissive_material", "add_plane", "add_sphere", "add_box", "create_mesh", "add_mesh", "set_sky", "set_ambient_light",
+    "add_emissive_material", "add_plane", "add_sphere", "add_box", "create_mesh", "create_mesh_ex", "add_mesh", "set_sky", "set_ambient_light",
     "set_skydome", "get_camera", "set_camera", "aim_camera", "aim_camera_at", "get_settings", "set_settings",
     "find_integrator", "load_reconstruction_kernel", "get_filter_cache", "set_filter_cache",
     "create_scene_bvh", "get_scene_bvh", "get_mesh_bvh", "get_counts",
@@ -132,6 +133,7 @@ def bind_host_scene(lib, prefix):
         "add_sphere": (C.c_uint32, [vp, C.c_uint32, C.c_float, P(M4x4Inv)]),
         "add_box": (C.c_uint32, [vp, C.c_uint32, c_float3, P(M4x4Inv)]),
         "create_mesh": (C.c_uint32, [vp, C.c_uint32, P(C.c_float), P(C.c_float)]),
+        "create_mesh_ex": (C.c_uint32, [vp, C.c_uint32, P(C.c_float), P(C.c_float), C.c_int32]),
         "add_mesh": (C.c_uint32, [vp, C.c_uint32, C.c_uint32, P(M4x4Inv)]),
         "set_sky": (C.c_int, [vp, c_float3, c_float3]),
         "set_ambient_light": (C.c_int, [vp, c_float3]),
@@ -229,13 +231,17 @@ class HostScene:
     def add_box(self, material, r, transform=None):
         return self.api.add_box(self.handle, material, _f3(r), self._xf(transform))
 
-    def create_mesh(self, positions, normals=None):
+    def create_mesh(self, positions, normals=None, method=None):
+        """method: None = the default build (SAH binned), or BVH_MIDPOINT_SPLIT / BVH_SAH_BINNED / BVH_SAH_FULL (bvh.h:7-11)"""
         pos = np.ascontiguousarray(positions, dtype=np.float32).reshape(-1, 9)
         nrm = None
         if normals is not None:
             nrm = np.ascontiguousarray(normals, dtype=np.float32).reshape(-1, 9)
             assert nrm.shape == pos.shape
-        h = self.api.create_mesh(self.handle, pos.shape[0], _fptr(pos), _fptr(nrm) if nrm is not None else None)
+        if method is None:
+            h = self.api.create_mesh(self.handle, pos.shape[0], _fptr(pos), _fptr(nrm) if nrm is not None else None)
+        else:
+            h = self.api.create_mesh_ex(self.handle, pos.shape[0], _fptr(pos), _fptr(nrm) if nrm is not None else None, int(method))
         if h == 0xFFFFFFFF:
             raise RuntimeError("create_mesh failed")
         return h

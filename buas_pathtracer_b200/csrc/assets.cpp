@@ -151,7 +151,8 @@ const float* bpt_obj_texcoords(const bpt_obj* o) { return o && o->has_texcoords 
 
 uint32_t bpt_create_mesh_from_obj(bpt_scene* s, const bpt_obj* o) {
     if (!s || !o || o->triangle_count == 0) { set_error("bpt_create_mesh_from_obj: empty mesh"); return 0xFFFFFFFFu; }
-    return bpt_create_mesh(s, o->triangle_count, o->positions.data(), o->has_normals ? o->normals.data() : nullptr);
+    // load_mesh (raytracer.cpp:148-158) builds file meshes with the midpoint-split BVH, not the binned-SAH one
+    return bpt_create_mesh_ex(s, o->triangle_count, o->positions.data(), o->has_normals ? o->normals.data() : nullptr, BPT_BVH_MIDPOINT_SPLIT);
 }
 
 int bpt_parse_hdr(const char* data, size_t size, uint32_t* out_w, uint32_t* out_h, float* pixels) {

@@ -62,6 +62,8 @@ struct BinAcc {
     Box3 bounds;
 };
 
+uint32_t hoare_partition(SortEntry* e, uint32_t count, float split_p, uint32_t axis);
+
 // Returns the split index (0 = "no split") and writes the axis.  bvh.cpp:138-213 + :26-51.
 uint32_t partition_sah_binned(SortEntry* e, uint32_t count, const Box3& bv, const Box3& cr, uint32_t* out_axis) {
     float parent_sah = (float)count*surface_area(bv);
@@ -120,9 +122,13 @@ uint32_t partition_sah_binned(SortEntry* e, uint32_t count, const Box3& bv, cons
     if (!(best_sah < parent_sah)) return 0;
     *out_axis = axis;
 
-    // Hoare partition around split_p.  The reference's scans are unguarded; running past either end of the
-    // range can only end in "split_index == 0" or "split_index > count-1", both of which mean "make a leaf"
-    // (bvh.cpp:254) and neither of which swaps anything, so the guarded scans below are equivalent.
+    return hoare_partition(e, count, split_p, axis);
+}
+
+// The Hoare partition of bvh.cpp:26-51 around (split_p, axis).  The reference's scans are unguarded; running past either
+// end of the range can only end in "split_index == 0" or "split_index > count-1", both of which mean "make a leaf"
+// (bvh.cpp:254) and neither of which swaps anything, so the guarded scans are equivalent.
+uint32_t hoare_partition(SortEntry* e, uint32_t count, float split_p, uint32_t axis) {
     int64_t i = -1, j = (int64_t)count;
     for (;;) {
         do { ++i; } while (i < (int64_t)count && e[i].p[axis] < split_p);
@@ -134,13 +140,54 @@ uint32_t partition_sah_binned(SortEntry* e, uint32_t count, const Box3& bv, cons
     return (uint32_t)i;
 }
 
+// partition_objects_midpoint_split (bvh.cpp:53-62): largest axis of the BOUNDS, pivot at their centre
+uint32_t partition_midpoint(SortEntry* e, uint32_t count, const Box3& bv, uint32_t* out_axis) {
+    uint32_t axis = largest_axis(bv);
+    float pivot = 0.5f*(bv.lo[axis] + bv.hi[axis]);
+    *out_axis = axis;
+    return hoare_partition(e, count, pivot, axis);
+}
+
+// partition_objects_sah + evaluate_sah (bvh.cpp:64-136): every centroid is a candidate plane, O(n^2)
+uint32_t partition_sah_full(SortEntry* e, uint32_t count, const Box3& bv, const Box3& cr, uint32_t* out_axis) {
+    float parent_sah = (float)count*surface_area(bv);
+    float best_sah = parent_sah;
+    float best_split_p = 0.0f;
+    uint32_t best_axis = 0;
+    uint32_t axis = largest_axis(cr);
+    for (uint32_t c = 0; c < count; ++c) {
+        float split_p = e[c].p[axis];
+        uint32_t l_count = 0, r_count = 0;
+        Box3 l, r;
+        l.invert(); r.invert();
+        for (uint32_t i = 0; i < count; ++i) {
+            Box3& side = e[i].p[axis] <= split_p ? l : r;
+            if (e[i].p[axis] <= split_p) ++l_count; else ++r_count;
+            for (int k = 0; k < 3; ++k) {
+                side.lo[k] = fmin_t(side.lo[k], e[i].p[k] - e[i].r[k]);
+                side.hi[k] = fmax_t(side.hi[k], e[i].p[k] + e[i].r[k]);
+            }
+        }
+        float l_sah = surface_area(l)*(float)l_count;
+        float r_sah = surface_area(r)*(float)r_count;
+        float sah = l_sah + r_sah;
+        if (best_sah > sah) { best_sah = sah; best_split_p = split_p; best_axis = axis; }
+    }
+    *out_axis = 0;
+    if (!(best_sah < parent_sah)) return 0;
+    *out_axis = best_axis;
+    return hoare_partition(e, count, best_split_p, best_axis);
+}
+
 struct BuildTask {
     uint32_t node, first, count;
 };
 
 } // namespace
 
-void build_bvh_sah_binned(std::vector<SortEntry>& entries, HostBVH* out) {
+void build_bvh_sah_binned(std::vector<SortEntry>& entries, HostBVH* out) { build_bvh(entries, out, BPT_BVH_SAH_BINNED); }
+
+void build_bvh(std::vector<SortEntry>& entries, HostBVH* out, int method) {
     uint32_t n = (uint32_t)entries.size();
     // construct_bvh_internal (bvh.cpp:289-326): 2N zeroed slots, root = 0, slot 1 skipped
     std::vector<bpt_bvh_node> nodes((size_t)2*n + 2);
@@ -176,7 +223,9 @@ void build_bvh_sah_binned(std::vector<SortEntry>& entries, HostBVH* out) {
         bool make_leaf = t.count <= kMaxLeaf;
         if (!make_leaf) {
             uint32_t axis = 0;
-            uint32_t split = partition_sah_binned(e, t.count, bv, cr, &axis);
+            uint32_t split = method == BPT_BVH_MIDPOINT_SPLIT ? partition_midpoint(e, t.count, bv, &axis)
+                           : method == BPT_BVH_SAH_FULL      ? partition_sah_full(e, t.count, bv, cr, &axis)
+                                                             : partition_sah_binned(e, t.count, bv, cr, &axis);
             if (split == 0 || split > t.count - 1) {
                 make_leaf = true;
             } else {
@@ -206,7 +255,9 @@ void build_bvh_sah_binned(std::vector<SortEntry>& entries, HostBVH* out) {
     for (uint32_t i = 0; i < n; ++i) out->indices[i] = entries[i].index;
 }
 
-void build_mesh_bvh(HostMesh* mesh) {
+void build_mesh_bvh(HostMesh* mesh) { build_mesh_bvh(mesh, BPT_BVH_SAH_BINNED); }
+
+void build_mesh_bvh(HostMesh* mesh, int method) {
     // create_bvh_for_mesh (bvh.cpp:342-391)
     uint32_t n = mesh->triangle_count;
     std::vector<SortEntry> entries(n);
@@ -222,7 +273,7 @@ void build_mesh_bvh(HostMesh* mesh) {
             s.r[k] = 0.5f*(hi - lo);
         }
     }
-    build_bvh_sah_binned(entries, &mesh->bvh);
+    build_bvh(entries, &mesh->bvh, method);
     mesh->leaf_triangles.resize((size_t)n*9);
     for (uint32_t i = 0; i < n; ++i) {
         memcpy(&mesh->leaf_triangles[(size_t)i*9], &mesh->positions[(size_t)mesh->bvh.indices[i]*9], 9*sizeof(float));

@@ -287,6 +287,21 @@ uint32_t bpt_create_mesh(bpt_scene* s, uint32_t triangle_count, const float* pos
     return (uint32_t)s->meshes.size() - 1;
 }
 
+uint32_t bpt_create_mesh_ex(bpt_scene* s, uint32_t triangle_count, const float* positions, const float* normals, int32_t method) {
+    if (method < BPT_BVH_MIDPOINT_SPLIT || method > BPT_BVH_SAH_FULL) { set_error("bpt_create_mesh_ex: unknown method %d", method); return 0xFFFFFFFFu; }
+    if (!positions || triangle_count == 0) { set_error("bpt_create_mesh_ex: empty mesh"); return 0xFFFFFFFFu; }
+    s->meshes.emplace_back();
+    HostMesh& m = s->meshes.back();
+    m.triangle_count = triangle_count;
+    m.positions.assign(positions, positions + (size_t)triangle_count*9);
+    if (normals) {
+        m.has_normals = true;
+        m.normals.assign(normals, normals + (size_t)triangle_count*9);
+    }
+    build_mesh_bvh(&m, method);
+    return (uint32_t)s->meshes.size() - 1;
+}
+
 uint32_t bpt_create_mesh_with_bvh(bpt_scene* s, uint32_t triangle_count, const float* positions, const float* normals,
                                   const bpt_bvh_node* nodes, uint32_t node_count, const uint32_t* indices) {
     if (!positions || triangle_count == 0 || !nodes || node_count == 0 || !indices) { set_error("bpt_create_mesh_with_bvh: null argument"); return 0xFFFFFFFFu; }

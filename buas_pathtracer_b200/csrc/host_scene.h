@@ -91,6 +91,8 @@ struct SortEntry {                       // BVHSortEntry (bvh.h:25-29)
 // bvh_build.cpp
 void build_bvh_sah_binned(std::vector<SortEntry>& entries, HostBVH* out);
 void build_mesh_bvh(HostMesh* mesh);
+void build_bvh(std::vector<SortEntry>& entries, HostBVH* out, int method);      // BPT_BVH_* (bvh.h:7-11)
+void build_mesh_bvh(HostMesh* mesh, int method);
 void build_scene_bvh(bpt_scene* scene);
 
 // host_scene.cpp

@@ -252,11 +252,18 @@ BPT_API uint32_t bpt_obj_triangle_count(const bpt_obj* obj);
 BPT_API const float* bpt_obj_positions(const bpt_obj* obj);                  /* 9 floats per triangle */
 BPT_API const float* bpt_obj_normals(const bpt_obj* obj);                    /* 9 floats per triangle, or NULL */
 BPT_API const float* bpt_obj_texcoords(const bpt_obj* obj);                  /* 9 floats per triangle, or NULL */
-BPT_API uint32_t bpt_create_mesh_from_obj(bpt_scene* s, const bpt_obj* obj); /* = bpt_create_mesh(positions, normals) */
+BPT_API uint32_t bpt_create_mesh_from_obj(bpt_scene* s, const bpt_obj* obj); /* load_mesh, raytracer.cpp:148-158: midpoint-split BVH */
 /* Radiance .hdr (32-bit_rle_rgbe): pixels == NULL only reports the size; otherwise w*h*3 floats, row order as the
  * reference stores them (Image_V3, assets.h:29-32). */
 BPT_API int bpt_parse_hdr(const char* data, size_t size, uint32_t* w, uint32_t* h, float* pixels);
 BPT_API int bpt_load_skydome_hdr(bpt_scene* s, const char* path);            /* parse + bpt_set_skydome */
+
+/* bpt_create_mesh with the construction method spelled out (BVHConstructionMethod, bvh.h:7-11).  bpt_create_mesh uses
+ * BPT_BVH_SAH_BINNED like create_scene_bvh (scene.cpp:208); the reference's load_mesh builds OBJ meshes with
+ * BPT_BVH_MIDPOINT_SPLIT (raytracer.cpp:154).  BPT_BVH_SAH_FULL is O(n^2), as in the reference. */
+enum { BPT_BVH_MIDPOINT_SPLIT = 0, BPT_BVH_SAH_BINNED = 1, BPT_BVH_SAH_FULL = 2 };
+BPT_API uint32_t bpt_create_mesh_ex(bpt_scene* s, uint32_t triangle_count, const float* positions, const float* normals,
+                                    int32_t method);
 
 /* bpt_create_mesh with a BVH supplied by the caller (e.g. from bpt_build_mesh_bvh_device) instead of the host build. */
 BPT_API uint32_t bpt_create_mesh_with_bvh(bpt_scene* s, uint32_t triangle_count, const float* positions, const float* normals,

@@ -24,6 +24,7 @@ BPT_API uint32_t ref_add_plane (ref_scene* s, uint32_t mat, const float n[3], fl
 BPT_API uint32_t ref_add_sphere(ref_scene* s, uint32_t mat, float r, const bpt_m4x4inv* xf);
 BPT_API uint32_t ref_add_box   (ref_scene* s, uint32_t mat, const float r[3], const bpt_m4x4inv* xf);
 BPT_API uint32_t ref_create_mesh(ref_scene* s, uint32_t triangle_count, const float* positions, const float* normals);
+BPT_API uint32_t ref_create_mesh_ex(ref_scene* s, uint32_t triangle_count, const float* positions, const float* normals, int32_t method);
 BPT_API uint32_t ref_add_mesh  (ref_scene* s, uint32_t mat, uint32_t mesh, const bpt_m4x4inv* xf);
 BPT_API int ref_set_sky(ref_scene* s, const float top[3], const float bot[3]);
 BPT_API int ref_set_ambient_light(ref_scene* s, const float rgb[3]);

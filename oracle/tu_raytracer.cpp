@@ -92,6 +92,10 @@ BPT_API uint32_t ref_add_box(ref_scene* s, uint32_t mat, const float r[3], const
 }
 
 BPT_API uint32_t ref_create_mesh(ref_scene* s, uint32_t triangle_count, const float* positions, const float* normals) {
+    return ref_create_mesh_ex(s, triangle_count, positions, normals, (int32_t)BVH_SAHBinned);
+}
+
+BPT_API uint32_t ref_create_mesh_ex(ref_scene* s, uint32_t triangle_count, const float* positions, const float* normals, int32_t method) {
     Scene* scene = &s->scene;
     Mesh mesh = {};
     mesh.has_normals = normals ? 1 : 0;
@@ -102,7 +106,7 @@ BPT_API uint32_t ref_create_mesh(ref_scene* s, uint32_t triangle_count, const fl
     if (normals) memcpy(mesh.triangles + triangle_count, normals, sizeof(Triangle)*(usize)triangle_count);
     // same call create_scene_bvh would make lazily (scene.cpp:208); done up front so instances share it,
     // like load_mesh does for the dragon (raytracer.cpp:150-159)
-    mesh.bvh = create_bvh_for_mesh(mesh.triangle_count, mesh.triangles, &scene->arena, &s->temp, BVH_SAHBinned, BVHStorage_Scalar);
+    mesh.bvh = create_bvh_for_mesh(mesh.triangle_count, mesh.triangles, &scene->arena, &s->temp, (BVHConstructionMethod)method, BVHStorage_Scalar);
     s->meshes.push_back(mesh);
     return (uint32_t)(s->meshes.size() - 1);
 }

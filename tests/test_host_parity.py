@@ -100,6 +100,24 @@ def test_mesh_bvh_degenerate_inputs(bpt, oracle):
         assert na.tobytes() == nb.tobytes() and np.array_equal(ia, ib) and ta.tobytes() == tb.tobytes()
 
 
+@pytest.mark.parametrize("method,levels", [(capi.BVH_MIDPOINT_SPLIT, [0, 2, 4, 6]), (capi.BVH_SAH_FULL, [0, 2, 3])])
+def test_mesh_bvh_other_construction_methods_bit_exact(bpt, oracle, method, levels):
+    """BVH_MidpointSplit (what the reference's load_mesh uses for OBJ files, raytracer.cpp:154) and BVH_SAHFull
+    (bvh.cpp:53-136), plus their degenerate cases (all centroids on one side of the midpoint, coincident centroids)"""
+    rng = np.random.RandomState(5)
+    base = rng.rand(1, 9).astype(np.float32)
+    inputs = [bpt.lib.make_displaced_icosphere(level, 0.08) for level in levels]
+    inputs += [np.repeat(base, 23, axis=0),
+               np.concatenate([np.repeat(base, 30, axis=0), base + np.float32(100.0)]),          # one far outlier: lopsided midpoint
+               (rng.rand(500, 9).astype(np.float32) ** 6) * np.float32(50.0)]                      # heavily skewed distribution
+    for tris in inputs:
+        a, b = bpt.Scene(), oracle.RefScene()
+        na, ia, ta = a.mesh_bvh(a.create_mesh(tris, method=method))
+        nb, ib, tb = b.mesh_bvh(b.create_mesh(tris, method=method))
+        assert na.shape == nb.shape and na.tobytes() == nb.tobytes(), f"method {method}, {tris.shape[0]} triangles: nodes differ"
+        assert np.array_equal(ia, ib) and ta.tobytes() == tb.tobytes()
+
+
 def test_instanced_scene_tlas_bit_exact(bpt, oracle):
     a, b = build_both(bpt, oracle, scenes.c3_instances, 320, 180, level=2, grid=4, sky_size=(64, 32))
     na, ia = a.scene_bvh()
