@@ -717,6 +717,9 @@ BPT_D void shade_path(const DScene& sc, const DPathState& st, const BatchDesc& b
 #ifndef BPT_SHADE_SORT
 #define BPT_SHADE_SORT 1
 #endif
+#ifndef BPT_SHADE_SORT_MATERIAL
+#define BPT_SHADE_SORT_MATERIAL 0     // measured on B200: shade time C2 +0.8 %, C3 -2.5 %, C4 +4 % -> off (the kernel is bound by
+#endif                                // path-state traffic, not by branch divergence; parity tests pass with it on)
 __global__ void __launch_bounds__(BPT_SHADE_THREADS, BPT_SHADE_MIN_CTAS)
 k_shade(DScene sc, DPathState st, BatchDesc b, uint32_t bounce,
         const uint32_t* __restrict__ in_queue, const uint32_t* __restrict__ n_ptr, uint32_t n_fixed,
@@ -736,10 +739,40 @@ k_shade(DScene sc, DPathState st, BatchDesc b, uint32_t bounce,
         if (threadIdx.x < 8) s_count[threadIdx.x] = 0;
         __syncthreads();
 
-        if (i < n) {
-            slot = in_queue ? in_queue[i] : i;
-            shade_path(sc, st, b, bounce, slot, alive, want_shadow, sh, octant);
+        bool have = i < n;
+        if (have) slot = in_queue ? in_queue[i] : i;
+#if BPT_SHADE_SORT_MATERIAL
+        // Sort-by-material: from the second bounce on the queue order is a mix of misses (sky lookup only), light hits
+        // (path ends) and the materials of the scene.  The block re-deals its entries so that neighbouring lanes shade the
+        // same kind of hit: key = miss | material id (folded to 3 bits), counting sort in shared memory.  The first
+        // bounce runs in pixel order, which is coherent already.
+        if (in_queue) {
+            uint32_t key = 0;
+            if (have) {
+                uint32_t prim = __float_as_uint(st.hit[slot].y);
+                if (prim != BPT_HIT_MISS) {
+                    uint32_t mat = (prim & BPT_HIT_PLANE) ? __ldg(&sc.planes[prim & ~BPT_HIT_PLANE].material)
+                                                          : __ldg(&sc.primitives[prim].material);
+                    key = 1u + (mat % 7u);
+                }
+            }
+            uint32_t r = 0;
+            if (have) r = atomicAdd(&s_count[key], 1u);
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                uint32_t run = 0;
+                for (int k = 0; k < 8; ++k) { s_start[k] = run; run += s_count[k]; s_count[k] = 0; }
+                s_base = run;                                    // entries this block holds in this round
+            }
+            __syncthreads();
+            if (have) s_slots[s_start[key] + r] = slot;
+            __syncthreads();
+            have = threadIdx.x < s_base;
+            if (have) slot = s_slots[threadIdx.x];
+            __syncthreads();
         }
+#endif
+        if (have) shade_path(sc, st, b, bounce, slot, alive, want_shadow, sh, octant);
 #if !BPT_SHADE_SORT
         octant = 0;
 #endif
@@ -761,7 +794,7 @@ k_shade(DScene sc, DPathState st, BatchDesc b, uint32_t bounce,
 
         uint32_t si = queue_append(shadow_count, want_shadow);
         if (want_shadow) shadow_items[si] = sh;
-        n_rays += (i < n ? 1u : 0u) + (want_shadow ? 1u : 0u);
+        n_rays += (have ? 1u : 0u) + (want_shadow ? 1u : 0u);
         n_shadow += want_shadow ? 1u : 0u;
         __syncthreads();
     }
