@@ -704,15 +704,15 @@ BPT_D void shade_path(const DScene& sc, const DPathState& st, const BatchDesc& b
 
 // One bounce for every active path of the batch (wavefront form of the loop at integrators.cpp:612-818).
 // Survivors are appended to the next bounce's queue GROUPED BY THE OCTANT OF THEIR NEW DIRECTION: a block sorts its (up
-// to 512) survivors by octant in shared memory and appends them with one atomic.  Neighbouring queue entries already
+// to 256) survivors by octant in shared memory and appends them with one atomic.  Neighbouring queue entries already
 // start from neighbouring surface points (the queue follows pixel order); with equal direction signs they also take the
 // same near/far decisions at every node, so the lanes of a traversal warp stay in the same phase for longer.  The order
 // of the queue does not enter any per-path result.
 #ifndef BPT_SHADE_THREADS
-#define BPT_SHADE_THREADS 512
+#define BPT_SHADE_THREADS 256     // 512: +2 % shade time (ncu: the sort's barriers are the top stall), 1024: +8 %
 #endif
 #ifndef BPT_SHADE_MIN_CTAS
-#define BPT_SHADE_MIN_CTAS 2      // x 512 threads = 64 registers: measured 14.7 ms vs 18.6 ms at 128 registers on C2 (latency-bound on path state)
+#define BPT_SHADE_MIN_CTAS 4      // x 256 threads = 64 registers: measured 14.7 ms vs 18.6 ms at 128 registers on C2 (latency-bound on path state)
 #endif
 #ifndef BPT_SHADE_SORT
 #define BPT_SHADE_SORT 1
