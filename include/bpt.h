@@ -241,7 +241,7 @@ BPT_API int bpt_get_mesh_bvh(const bpt_scene* s, uint32_t mesh, const bpt_bvh_no
                              const uint32_t** indices, uint32_t* index_count,
                              const float** leaf_order_triangles /* 9 floats each */);
 /* ---- asset readers: the reference's parse_obj (Raytracer/assets.cpp:187-400) and parse_hdr (:411-600),
- * same input -> same triangles / texels, quirks included (see csrc/assets.cpp).  Malformed input that would make the
+ * same input -> same triangles / texels, quirks included (see csrc/obj_hdr_readers.cpp).  Malformed input that would make the
  * reference read out of bounds or loop forever returns an error here. */
 typedef struct bpt_obj bpt_obj;
 enum { BPT_WINDING_CLOCKWISE = 0, BPT_WINDING_COUNTER_CLOCKWISE = 1 };        /* MeshWinding, assets.h:74-77 */
