@@ -862,12 +862,17 @@ int bpt_resolve_bgra8(bpt_ctx* ctx, const bpt_post_settings* post, const uint8_t
     return BPT_OK;
 }
 
-int bpt_build_mesh_bvh_device(bpt_ctx* ctx, uint32_t n, const float* positions, bpt_bvh_node* nodes_out,
+int bpt_build_mesh_bvh_device(bpt_ctx* ctx, uint32_t n, const float* positions, int32_t method, bpt_bvh_node* nodes_out,
                               uint32_t node_capacity, uint32_t* node_count, uint32_t* indices_out, float* build_ms) {
     using namespace bpt::gbvh;
     static_assert(sizeof(OutNode) == sizeof(bpt_bvh_node), "node layout");
     if (!ctx || !positions || !nodes_out || !node_count || !indices_out || n == 0) { set_error("bpt_build_mesh_bvh_device: null argument"); return BPT_ERR_ARG; }
-    if (node_capacity < 2ull*n + 2 && node_capacity < 2) { set_error("bpt_build_mesh_bvh_device: node buffer too small"); return BPT_ERR_ARG; }
+    if (node_capacity < 2) { set_error("bpt_build_mesh_bvh_device: node buffer too small"); return BPT_ERR_ARG; }
+    if (method != BPT_BVH_SAH_BINNED && method != BPT_BVH_MIDPOINT_SPLIT) {
+        set_error("bpt_build_mesh_bvh_device: method %d is not built on the device (BPT_BVH_SAH_FULL is O(n^2), host only)", method);
+        return BPT_ERR_UNSUPPORTED;
+    }
+    const int midpoint = method == BPT_BVH_MIDPOINT_SPLIT ? 1 : 0;
     CK(cudaSetDevice(ctx->device));
     cudaStream_t s = ctx->stream;
     const uint32_t T = 256;
@@ -907,16 +912,18 @@ int bpt_build_mesh_bvh_device(bpt_ctx* ctx, uint32_t n, const float* positions, 
     int cur = 0;
     uint64_t launches = 2;
     while (lvl_count > 0 && err == cudaSuccess) {
-        if (levels.size() >= 512 || lvl_count > max_level_nodes) { err = cudaErrorUnknown; break; }
+        if (levels.size() >= 65536 || lvl_count > max_level_nodes) { err = cudaErrorUnknown; break; }    // deeper than any tree of <= 2^32 entries can be split sensibly
         levels.push_back({lvl_start, lvl_count});
         GNode* lv = d_nodes + lvl_start;
         uint32_t next_base = lvl_start + lvl_count;
         cudaMemsetAsync(d_next, 0, 4, s);
         k_init_acc<<<blocks(lvl_count), T, 0, s>>>(d_acc, lvl_count);
         k_bounds<<<blocks(n), T, 0, s>>>(d_e[cur], d_seg[cur], n, d_acc);
-        k_decide<<<blocks(lvl_count), T, 0, s>>>(lv, d_acc, lvl_count);
-        k_bin<<<blocks(n), T, 0, s>>>(d_e[cur], d_seg[cur], n, d_acc);
-        k_sah<<<blocks(lvl_count), T, 0, s>>>(lv, d_acc, lvl_count);
+        k_decide<<<blocks(lvl_count), T, 0, s>>>(lv, d_acc, lvl_count, midpoint);
+        if (!midpoint) {
+            k_bin<<<blocks(n), T, 0, s>>>(d_e[cur], d_seg[cur], n, d_acc);
+            k_sah<<<blocks(lvl_count), T, 0, s>>>(lv, d_acc, lvl_count);
+        }
         k_flags<<<blocks(n), T, 0, s>>>(d_e[cur], d_seg[cur], n, d_acc, d_flags, d_perm);
         k_scan_tiles<<<tiles, kScanBlock, 0, s>>>(d_flags, n, d_scan, d_tiles);
         k_scan_tile_sums<<<1, 1024, 0, s>>>(d_tiles, tiles, d_scan, n);

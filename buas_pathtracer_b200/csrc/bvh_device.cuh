@@ -172,7 +172,7 @@ __global__ void k_bounds(const GEntry* __restrict__ e, const uint32_t* __restric
 }
 
 // bv_p / bv_r, the leaf test, and the binning parameters (bvh.cpp:233-236, :141-155)
-__global__ void k_decide(GNode* nodes, GAcc* acc, uint32_t count) {
+__global__ void k_decide(GNode* nodes, GAcc* acc, uint32_t count, int midpoint) {
     uint32_t j = blockIdx.x*blockDim.x + threadIdx.x;
     if (j >= count) return;
     GNode& nd = nodes[j];
@@ -185,6 +185,13 @@ __global__ void k_decide(GNode* nodes, GAcc* acc, uint32_t count) {
     }
     nd.child = kInvalid; nd.axis = 0;
     if (nd.count <= kMaxLeaf) { a.state = 0; return; }
+    if (midpoint) {                     // partition_objects_midpoint_split (bvh.cpp:53-62): no binning, no SAH test
+        uint32_t ax = largest_axis(bv);
+        a.axis = ax;
+        a.split_p = 0.5f*(bv.lo[ax] + bv.hi[ax]);
+        a.state = 2;
+        return;
+    }
     uint32_t axis = largest_axis(cr);
     a.axis = axis;
     a.k0 = cr.lo[axis];

@@ -97,7 +97,7 @@ def load_library():
     L.bpt_set_tail_threshold.restype = C.c_int
     L.bpt_set_tail_threshold.argtypes = [vp, C.c_uint32]
     L.bpt_build_mesh_bvh_device.restype = C.c_int
-    L.bpt_build_mesh_bvh_device.argtypes = [vp, C.c_uint32, vp, vp, C.c_uint32, P(C.c_uint32), vp, P(C.c_float)]
+    L.bpt_build_mesh_bvh_device.argtypes = [vp, C.c_uint32, vp, C.c_int32, vp, C.c_uint32, P(C.c_uint32), vp, P(C.c_float)]
     L.bpt_get_transfer_bytes.restype = C.c_int
     L.bpt_get_transfer_bytes.argtypes = [vp, P(C.c_uint64), P(C.c_uint64), C.c_int]
     L.bpt_resolve_bgra8.restype = C.c_int
@@ -290,14 +290,14 @@ class Renderer:
     def set_detailed_timing(self, on=True):
         _check(self.lib.bpt_set_detailed_timing(self.handle, int(on)), "bpt_set_detailed_timing")
 
-    def build_mesh_bvh(self, positions):
+    def build_mesh_bvh(self, positions, method=capi.BVH_SAH_BINNED):
         """create_bvh_for_mesh on the device: (nodes, leaf-order indices, device milliseconds)"""
         pos = np.ascontiguousarray(positions, dtype=np.float32).reshape(-1, 9)
         n = pos.shape[0]
         nodes = np.zeros(2 * n + 2, dtype=capi.BVH_NODE_DTYPE)
         idx = np.zeros(n, dtype=np.uint32)
         nc, ms = C.c_uint32(), C.c_float()
-        _check(self.lib.bpt_build_mesh_bvh_device(self.handle, n, pos.ctypes.data, nodes.ctypes.data, nodes.shape[0],
+        _check(self.lib.bpt_build_mesh_bvh_device(self.handle, n, pos.ctypes.data, int(method), nodes.ctypes.data, nodes.shape[0],
                                                   C.byref(nc), idx.ctypes.data, C.byref(ms)), "bpt_build_mesh_bvh_device")
         return nodes[:nc.value].copy(), idx, ms.value
 

@@ -113,11 +113,11 @@ static int build_obj_scene(bpt_scene* s, bpt_ctx* ctx, uint32_t w, uint32_t h, c
     const float up[3] = {0, 1, 0};
     bpt_add_plane(s, ground, up, 0.0f);
     uint32_t mesh;
-    if (gpu_bvh) {      // create_bvh_for_mesh on the device, same arrays as the host build
+    if (gpu_bvh) {      // create_bvh_for_mesh(BVH_MidpointSplit) like load_mesh (raytracer.cpp:154), on the device: same arrays as the host build
         std::vector<bpt_bvh_node> nodes((size_t)2*n + 2);
         std::vector<uint32_t> order(n);
         uint32_t node_count = 0; float ms = 0;
-        if (bpt_build_mesh_bvh_device(ctx, n, pos, nodes.data(), (uint32_t)nodes.size(), &node_count, order.data(), &ms) != BPT_OK) { fprintf(stderr, "%s\n", bpt_last_error()); return 1; }
+        if (bpt_build_mesh_bvh_device(ctx, n, pos, BPT_BVH_MIDPOINT_SPLIT, nodes.data(), (uint32_t)nodes.size(), &node_count, order.data(), &ms) != BPT_OK) { fprintf(stderr, "%s\n", bpt_last_error()); return 1; }
         printf("device BVH build: %u triangles -> %u nodes in %.2f ms\n", n, node_count, ms);
         mesh = bpt_create_mesh_with_bvh(s, n, pos, bpt_obj_normals(obj), nodes.data(), node_count, order.data());
     } else {

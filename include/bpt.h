@@ -361,7 +361,7 @@ BPT_API int bpt_set_tail_threshold(bpt_ctx* ctx, uint32_t paths);
  * included) and same leaf-order indices as bpt_create_mesh / the reference produce on the host.  nodes_out needs room for
  * 2*triangle_count + 2 nodes.  build_ms (nullable) receives the device time of the build (entries resident). */
 BPT_API int bpt_build_mesh_bvh_device(bpt_ctx* ctx, uint32_t triangle_count, const float* positions,
-                                      bpt_bvh_node* nodes_out, uint32_t node_capacity, uint32_t* node_count,
+                                      int32_t method /* BPT_BVH_SAH_BINNED or BPT_BVH_MIDPOINT_SPLIT */, bpt_bvh_node* nodes_out, uint32_t node_capacity, uint32_t* node_count,
                                       uint32_t* indices_out, float* build_ms);
 
 /* cumulative bytes this context copied host->device / device->host (scene uploads, rays, film, records) */

@@ -10,9 +10,9 @@ from buas_pathtracer_b200 import capi, lib, scenes
 pytestmark = pytest.mark.gpu
 
 
-def host_build(tris):
+def host_build(tris, method=None):
     s = B.Scene()
-    m = s.create_mesh(tris)
+    m = s.create_mesh(tris, method=method)
     nodes, idx, _ = s.mesh_bvh(m)
     return nodes, idx
 
@@ -33,6 +33,21 @@ def test_device_bvh_equals_host_bvh_icosphere(renderer, level):
     hn, hi = host_build(tris)
     assert_same_bvh(dn, di, hn, hi, f"icosphere level {level}")
     print(f"icosphere level {level}: {tris.shape[0]} triangles, {dn.shape[0]} nodes, device build {ms:.2f} ms")
+
+
+@pytest.mark.parametrize("level", [0, 2, 4, 6, 8])
+def test_device_midpoint_bvh_equals_host(renderer, level):
+    """BVH_MidpointSplit (what the reference builds for OBJ files, raytracer.cpp:154) on the device"""
+    tris = lib.make_displaced_icosphere(level)
+    dn, di, ms = renderer.build_mesh_bvh(tris, capi.BVH_MIDPOINT_SPLIT)
+    hn, hi = host_build(tris, capi.BVH_MIDPOINT_SPLIT)
+    assert_same_bvh(dn, di, hn, hi, f"midpoint, icosphere level {level}")
+    rng = np.random.RandomState(level)
+    soup = np.ascontiguousarray((rng.rand(3000, 9) ** 5) * 40, np.float32)         # skewed: lopsided midpoints, forced leaves
+    dn, di, _ = renderer.build_mesh_bvh(soup, capi.BVH_MIDPOINT_SPLIT)
+    hn, hi = host_build(soup, capi.BVH_MIDPOINT_SPLIT)
+    assert_same_bvh(dn, di, hn, hi, "midpoint, skewed soup")
+    print(f"midpoint level {level}: {tris.shape[0]} triangles, device build {ms:.2f} ms")
 
 
 def test_device_bvh_degenerate_inputs(renderer):
