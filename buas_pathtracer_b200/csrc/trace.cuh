@@ -146,6 +146,9 @@ struct TraceCounters {   // per-thread, flushed by the caller
     uint32_t tlas_pops, instances, mesh_calls, blas_pops, blas_inner, blas_leaves, tris;
 };
 
+#ifndef BPT_STACK_TOP_IN_REGS
+#define BPT_STACK_TOP_IN_REGS 0
+#endif
 #define BPT_STACK_DEPTH 64     // the reference's node_stack[64] (intersection.cpp:261, :445), far children only here
 
 // Per-lane traversal state.  begin() does what precedes the reference's node loop (planes + TLAS root pop); the
@@ -237,6 +240,10 @@ BPT_D void persistent_trace(const DScene& sc, Src& src, uint32_t n, uint32_t* cu
     bool exhausted = false;
     uint32_t my_index = 0;
     const bool tame = sc.tame_bounds != 0;
+#if BPT_STACK_TOP_IN_REGS
+    float4 top = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    bool top_valid = false;          // entry tv.sp-1 is in `top`, entries below it are in stk
+#endif
     tv.occ = false;
     auto occlusion = [&]() { return MODE == TRACE_MODE_MIXED ? tv.occ : (MODE == TRACE_MODE_OCCLUSION); };
 
@@ -263,7 +270,14 @@ BPT_D void persistent_trace(const DScene& sc, Src& src, uint32_t n, uint32_t* cu
             }
             if (tv.sp == 0) { finish(); return; }
             --tv.sp;
+#if BPT_STACK_TOP_IN_REGS
+            // the newest entry lives in registers: a push that is popped before the next push never touches memory
+            float4 e;
+            if (top_valid) { e = top; top_valid = false; }
+            else e = stk.e[tv.sp];
+#else
             float4 e = stk.e[tv.sp];
+#endif
             if (e.z < tv.t) { tv.cur_lf = __float_as_uint(e.x); tv.cur_ca = __float_as_uint(e.y); classify(); return; }
         }
     };
@@ -296,6 +310,9 @@ BPT_D void persistent_trace(const DScene& sc, Src& src, uint32_t n, uint32_t* cu
                 if (src.next(o, d, max_t, ign, is_occ)) {       // false: the lane's path ended without another ray
                     tv.occ = is_occ;
                     tv.begin(sc, o, d, max_t, ign, ctr);
+#if BPT_STACK_TOP_IN_REGS
+                    top_valid = false;
+#endif
                     if (tv.done()) finish(); else classify();
                 }
             }
@@ -314,6 +331,9 @@ BPT_D void persistent_trace(const DScene& sc, Src& src, uint32_t n, uint32_t* cu
                     tv.occ = is_occ;
                     my_index = idx;
                     tv.begin(sc, o, d, max_t, ign, ctr);
+#if BPT_STACK_TOP_IN_REGS
+                    top_valid = false;
+#endif
                     if (tv.done()) finish(); else classify();
                 }
             }
@@ -345,7 +365,12 @@ BPT_D void persistent_trace(const DScene& sc, Src& src, uint32_t n, uint32_t* cu
                 if (STATS) { if (tv.level) { tv.c_pops += 2; tv.c_inner += 1; } else ctr.tlas_pops += 2; }
                 uint32_t near_lf = __float_as_uint(n1.z), near_ca = __float_as_uint(n1.w);
                 if (far_hit && tv.sp < BPT_STACK_DEPTH) {
+#if BPT_STACK_TOP_IN_REGS
+                    if (top_valid) stk.e[tv.sp - 1] = top;              // the previous newest entry moves to memory
+                    top = make_float4(f1.z, f1.w, far_tn, 0.0f); top_valid = true; ++tv.sp;
+#else
                     stk.e[tv.sp] = make_float4(f1.z, f1.w, far_tn, 0.0f); ++tv.sp;
+#endif
                 }
                 if (near_hit && near_tn < tv.t) { tv.cur_lf = near_lf; tv.cur_ca = near_ca; classify(); }
                 else pop();
