@@ -705,6 +705,7 @@ retry_shape:
             // they do not (C4 at 64 Mi slots: -15 %, the mixed population diverges more): merge below a batch size.
             const bool merged = !stats && ctx->merge_traces && b.slots <= ctx->merge_max_slots;
             const bool tail = !stats && ctx->tail_threshold > 0;
+            if (max_bounce > 0) { k_reset_counters<<<1, 32, 0, s>>>(counters, (1 << 3) | (1 << 4)); ctx->launches++; }   // fetch cursors; later bounces: k_bounce_prepare
             for (uint32_t bounce = 0; bounce < max_bounce; ++bounce) {
                 int in = bounce & 1, out = in ^ 1;
                 const uint32_t* in_queue = bounce == 0 ? nullptr : pp.q.active[in];
@@ -712,8 +713,6 @@ retry_shape:
                 uint32_t work = b.slots;    // upper bound; kernels read the true counts on the device
                 uint32_t tg = grid_for(ctx, work, 128, ctx->trace_ctas_per_sm);
 
-                k_reset_counters<<<1, 32, 0, s>>>(counters, (1 << 3) | (1 << 4));
-                ctx->launches++;
                 begin_span(ctx, ST_TRACE, s);
                 if (merged && bounce > 0) {
                     k_trace_merged<<<tg, 128, 0, s>>>(sc, pp.st, in_queue, in_count, pp.q.shadow, counters + 2, counters + 3, ctx->refill);
@@ -726,17 +725,16 @@ retry_shape:
                 end_span(ctx, s);
                 ctx->launches++; ctx->trace_launches++;
 
-                // the shadow items of the previous bounce are consumed (merged) or not yet produced: reset before shading
-                k_reset_counters<<<1, 32, 0, s>>>(counters, (1 << out) | (1 << 2));
+                // queue bookkeeping for the shade below, and -- few survivors -- the hand-over to k_tail, which finishes them
+                // inside one launch; the wavefront launches of the remaining bounces then find empty queues
+                k_bounce_prepare<<<1, 32, 0, s>>>(counters, in, out, (tail && bounce > 0) ? ctx->tail_threshold : 0u);
                 ctx->launches++;
                 if (tail && bounce > 0) {
-                    // few survivors: finish them inside one launch; the wavefront launches below then find empty queues
-                    k_tail_decide<<<1, 32, 0, s>>>(counters, in, ctx->tail_threshold);
                     begin_span(ctx, ST_TRACE, s);
                     k_tail<<<(ctx->tail_threshold + 127)/128, 128, 0, s>>>(sc, pp.st, b, bounce, pp.q.active[in], counters + 8, ctx->tail_refill, ctx->d_stats);
                     debug_sync("k_tail", bounce, s);
                     end_span(ctx, s);
-                    ctx->launches += 2; ctx->trace_launches++;
+                    ctx->launches++; ctx->trace_launches++;
                 }
                 begin_span(ctx, ST_SHADE, s);
                 k_shade<<<grid_for(ctx, work, BPT_SHADE_THREADS, 4), BPT_SHADE_THREADS, 0, s>>>(sc, pp.st, b, bounce, in_queue, in_count, b.slots,

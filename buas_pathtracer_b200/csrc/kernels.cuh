@@ -803,7 +803,7 @@ k_shade(DScene sc, DPathState st, BatchDesc b, uint32_t bounce,
 
 // ---------------------------------------------------------------------------------------------------------------
 // Fused tail.  Once only a few paths of a batch are still alive, a wavefront bounce costs the latency of its longest
-// ray four launches over (the machine is empty), bounce after bounce.  k_tail_decide (one thread, between the trace
+// ray four launches over (the machine is empty), bounce after bounce.  k_bounce_prepare (one thread, between the trace
 // and the shade of a bounce) hands the survivors over when they fit: it moves the active count to counters[8] and
 // zeroes it, so the remaining wavefront launches of the batch find empty queues.  k_tail then carries each surviving
 // path to its end inside ONE launch: lane = path, and shading is simply what an idle lane does to get its next rays
@@ -855,9 +855,13 @@ struct TailSrc {
     }
 };
 
-// counters: the batch's DQueues::counters; in = index of the active count of this bounce
-__global__ void k_tail_decide(uint32_t* counters, int in, uint32_t threshold) {
+// Between the trace and the shade of a bounce (one thread): (1) the bookkeeping that used to be two launches -- zero the
+// count of the queue the shade is about to fill, the shadow count (consumed by the merged trace, or not yet produced)
+// and both fetch cursors (this bounce's trace and the previous bounce's shadow trace are done with them); (2) the
+// hand-over to k_tail.  counters: the batch's DQueues::counters; in / out = active counts of this / the next bounce.
+__global__ void k_bounce_prepare(uint32_t* counters, int in, int out, uint32_t threshold) {
     if (threadIdx.x == 0) {
+        counters[out] = 0u; counters[2] = 0u; counters[3] = 0u; counters[4] = 0u;
         uint32_t n = counters[in];
         if (n != 0u && n <= threshold) { counters[8] = n; counters[in] = 0u; }
         else counters[8] = 0u;
