@@ -71,3 +71,25 @@ def test_host_scene_error_paths(bpt):
     fc = s.get_filter_cache()
     fc.kernel_size = 40
     assert s.api.set_filter_cache(s.handle, C.byref(fc)) != 0
+
+
+def test_new_host_entry_points_report_errors(bpt):
+    """bpt_create_mesh_ex / bpt_create_mesh_with_bvh / bpt_parse_obj / bpt_parse_hdr: bad input -> error code + message, never a crash"""
+    import numpy as np
+    from buas_pathtracer_b200 import capi, lib
+    s = bpt.Scene()
+    tri = np.array([[0, 0, 0, 1, 0, 0, 0, 1, 0]], np.float32)
+    with pytest.raises(RuntimeError):
+        s.create_mesh(tri, method=7)                                   # unknown construction method
+    assert "unknown method" in bpt.load_library().bpt_last_error().decode()
+    m = s.create_mesh(np.repeat(tri, 9, axis=0), method=capi.BVH_MIDPOINT_SPLIT)
+    nodes, idx, _ = s.mesh_bvh(m)
+    with pytest.raises(bpt.BptError):
+        s.create_mesh_with_bvh(np.repeat(tri, 9, axis=0), nodes, idx + 100)     # index outside the mesh
+    assert s.create_mesh_with_bvh(np.repeat(tri, 9, axis=0), nodes, idx) == m + 1
+    with pytest.raises(bpt.BptError):
+        lib.parse_obj("f 1 2 3\n", 1)                                           # indices into an empty vertex pool
+    with pytest.raises(bpt.BptError):
+        lib.parse_obj("v 0 0 0\n", 5)                                           # winding
+    with pytest.raises(bpt.BptError):
+        lib.parse_hdr(b"")                                                      # nothing at all
