@@ -285,9 +285,13 @@ BPT_D void persistent_trace(const DScene& sc, Src& src, uint32_t n, uint32_t* cu
     // The scheduling loop.  Its trip count is bounded on purpose: with a plain `for (;;)` whose only exit is the vote
     // below, nvcc 12.9 rotates the loop and peels its first iteration, and the resulting k_trace_merged hung on
     // B200 (deterministically, BASELINE config 4 at >= 16 spp: launch of bounce 3 never returned; every
-    // instrumented build ran through).  A second, never-taken exit at the loop head keeps the loop in its source
-    // shape; tests/test_gpu_golden_and_fullsize.py::test_no_hang_* pins the behaviour.
+    // instrumented build ran through, and so did the same PTX assembled with ptxas -O0; -O1 and above hang).  A second,
+    // never-taken exit at the loop head keeps the loop in its source shape; tests/test_gpu_golden_and_fullsize.py::test_no_hang_* pins the behaviour.
+#ifdef BPT_DBG_PLAIN_LOOP            /* reproduces the hang described above; for investigating it only */
+    for (;;) {
+#else
     for (unsigned long long trips = 0; trips != ~0ull; ++trips) {
+#endif
         // phase populations of the warp, one byte each, from a single warp-wide add (REDUX.SUM)
         // (an idle lane that cannot get another ray votes for nothing)
         bool can_fetch;
