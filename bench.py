@@ -8,7 +8,7 @@ every pixel of the frame x its samples-per-pixel through ray generation, TLAS/BL
 Russian roulette and the Mitchell-Netravali splat.  N=1 renders BASELINE config 2 (1,310,720-triangle displaced
 icosphere, 1920x1080, 64 spp).  With N>1 (torchrun, one rank per GPU) the same frame is split into interleaved
 64-row blocks over the ranks, the scene is replicated, and the partial films are summed with ONE NCCL reduce per
-pass (strong scaling).
+pass by the library itself (bpt_reduce_film, include/bpt.h section 3; strong scaling).
 
 `value`     device-timed whole-job Mrays/s with the scene resident in HBM (CUDA events, max over ranks).
 `e2e`       the same metric through the public C-ABI with host buffers: every step re-uploads the host scene
@@ -113,23 +113,46 @@ def algorithmic_bytes(st, shadow):
     return BYTES_NODE * tl + BYTES_INSTANCE * inst + BYTES_NODE * bl + BYTES_TRI * tri
 
 
-def cpu_reference_run(cfg_key, w, h, seconds_target=15.0, threads=None, scale_div=1):
+def reference_scene(cfg_key, w, h):
+    """The configuration's scene inside the reference's own Scene (oracle/_ref).  Inputs come from the standalone
+    inputs library: nothing of the product (libbpt.so) is loaded on this path."""
+    from buas_pathtracer_b200 import scenes
+    from oracle import ref_oracle, ref_inputs
+    scenes.INPUTS = ref_inputs
+    ref = ref_oracle.RefScene()
+    scenes.CONFIGS[cfg_key]["build"](ref, w, h)
+    return ref
+
+
+def reference_rays_per_sample(ref, w, h, spp, rows=16):
+    """Rays per sample of the workload, counted by the REFERENCE itself (untimed): its single-threaded render with the
+    oracle's intersect_scene / intersect_shadow_ray call counter, on `rows` evenly spaced full rows of the frame at the
+    configuration's spp."""
+    total = n = 0
+    step = max(1, h // rows)
+    for y in range(step // 2, h, step):
+        _, rec = ref.render_parity(w, h, spp, rect=(0, y, w, y + 1), records=True)
+        total += int(rec["rays"].astype(np.int64).sum())
+        n += rec.shape[0]
+    return total / max(1, n), n
+
+
+def cpu_reference_run(cfg_key, w, h, seconds_target=15.0, threads=None, ref=None, spp=None):
     """Time the reference's own WorkQueue renderer (verbatim, per-tile seeding) on a bounded sample of the workload."""
     from buas_pathtracer_b200 import scenes
-    from oracle import ref_oracle
     cfg = scenes.CONFIGS[cfg_key]
     nproc = os.cpu_count() or 1
     if threads is None:
         threads = nproc + nproc // 4                       # raytracer.cpp:1580-1592
-    ref = ref_oracle.RefScene()
-    cfg["build"](ref, w, h)
-    # calibrate with 1 spp on a reduced frame, then size spp for ~seconds_target of CPU work
-    cw, ch = max(64, w // 4), max(36, h // 4)
-    ref2 = ref_oracle.RefScene()
-    cfg["build"](ref2, cw, ch)
-    _, sec, _ = ref2.render_threaded(cw, ch, 1, threads, want_film=False)
-    rate = cw * ch / max(sec, 1e-6)
-    spp = int(max(1, min(cfg["spp"], round(rate * seconds_target / (w * h)))))
+    if ref is None:
+        ref = reference_scene(cfg_key, w, h)
+    if spp is None:
+        # calibrate with 1 spp on a reduced frame, then size spp for ~seconds_target of CPU work
+        cw, ch = max(64, w // 4), max(36, h // 4)
+        ref2 = reference_scene(cfg_key, cw, ch)
+        _, sec, _ = ref2.render_threaded(cw, ch, 1, threads, want_film=False)
+        rate = cw * ch / max(sec, 1e-6)
+        spp = int(max(1, min(cfg["spp"], round(rate * seconds_target / (w * h)))))
     _, sec, st = ref.render_threaded(w, h, spp, threads, want_film=False)
     samples = w * h * spp
     return {"seconds": sec, "samples": samples, "spp": spp, "threads": threads, "nproc": nproc,
@@ -161,29 +184,34 @@ def main():
 
     # ------------------------------------------------------------------------------------------------------------
     if args.impl == "reference":
+        # The reference's own CPU renderer (oracle/_ref = the reference's translation units compiled here, unmodified)
+        # through its own WorkQueue, all host threads, on this arm's config.  A step = one pass over the full frame at a
+        # bounded spp (stated in config["spp_per_step_run"]; samples/s of this renderer does not depend on spp).
+        # Nothing of the product is loaded: inputs come from oracle/_ref/libbpt_inputs.so, rays are counted by the
+        # reference's own call counter in an untimed pass.
         if rank != 0:
             return 0
+        ref = reference_scene(args.config, w, h)
+        rps, rps_n = reference_rays_per_sample(ref, w, h, spp)
         vals = []
         info = None
+        spp_run = None
         for i in range(args.warmup + args.steps):
-            info = cpu_reference_run(args.config, w, h, seconds_target=8.0)
+            info = cpu_reference_run(args.config, w, h, seconds_target=8.0, ref=ref, spp=spp_run)
+            spp_run = info["spp"]                      # calibrated once, then every step runs the same sample
             if i >= args.warmup:
                 vals.append(info)
         sec = float(np.mean([v["seconds"] for v in vals]))
         samples = vals[0]["samples"]
-        rps = float(os.environ.get("BPT_RAYS_PER_SAMPLE", "0")) or None
-        # rays/sample of this workload is a property of the integrator + scene; measured by the GPU arm's counters
-        # (parity tests show identical per-sample ray counts) and cached next to the bench for the reference arm.
-        cache = os.path.join(ROOT, "profiles", f"rays_per_sample_{args.config}.json")
-        if rps is None and os.path.exists(cache):
-            rps = json.load(open(cache))["rays_per_sample"]
-        if rps is None:
-            rps = 1.0
         value = samples * rps / sec / 1e6
+        config = dict(config, spp_per_step_run=info["spp"], l2_policy="n/a (CPU renderer)",
+                      partition="reference WorkQueue: 64x64 tiles over host threads (raytracer.cpp:551-757)",
+                      seeding="per-tile stream (raytracer.cpp:588-591)")
         line = {"impl": "reference", "metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": args.gpus,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
                 "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
                 "samples_per_s": samples / sec, "rays_per_sample": rps,
+                "rays_per_sample_source": f"counted by the reference (oracle call counter) on {rps_n} samples of this frame, untimed",
                 "cpu_baseline": {"value": value, "unit": "Mrays/s", "cores": info["threads"], "kind": "reference",
                                  "sample": f"{w}x{h} at {info['spp']} spp ({samples} samples) per step, verbatim WorkQueue "
                                            f"renderer, {info['threads']} worker threads on {info['nproc']} logical CPUs"},
@@ -207,19 +235,50 @@ def main():
     cfg["build"](scene, w, h)
     r = B.Renderer(local_rank)
     r.upload_scene(scene)
-    # the film lives in a torch tensor so the NCCL reduce can run on it in place
-    film = torch.zeros((h, w, 4), dtype=torch.float32, device=f"cuda:{local_rank}")
-    r.film_use_external(film.data_ptr(), w, h)
+    r.film_resize(w, h)
     bands = my_rows(h, rank, world)
 
-    def render(frame_count):
-        r.render_pass_bands(spp, bands, frame_count=frame_count)   # this rank's row blocks as one workload
+    # Multi-GPU lives in the library (include/bpt.h section 3): every rank accumulates its row blocks into its own
+    # film, bpt_reduce_film sums the films on rank 0 with ONE ncclReduce per progressive pass, enqueued on the
+    # library's stream right behind the pass (no host synchronisation in between).  torch.distributed only carries the
+    # NCCL id to the ranks, the barriers and the max-over-ranks of the timings.
+    comm = None
+    if dist is not None:
+        uid = torch.from_numpy(B.Renderer.nccl_unique_id() if rank == 0 else np.zeros(128, np.uint8)).to(f"cuda:{local_rank}")
+        dist.broadcast(uid, src=0)
+        comm = r.nccl_comm_init_rank(uid.cpu().numpy(), world, rank)
+
+    def render(frame_count, n_spp=spp):
+        r.render_pass_bands(n_spp, bands, frame_count=frame_count)   # this rank's row blocks as one workload
 
     def step(frame_count):
         render(frame_count)
+        if comm is not None:
+            r.reduce_film(comm, 0)                         # one collective per progressive pass, behind the pass on its stream
         r.sync()
-        if dist is not None:
-            dist.reduce(film, dst=0, op=dist.ReduceOp.SUM)     # one collective per progressive pass
+
+    # --- multi-GPU correctness on the hardware (untimed): the N-rank reduced film against rank 0 rendering the whole
+    #     frame alone, same seeds; they differ only in the order of float additions (atomics + the reduce)
+    multi_gpu_check = None
+    if comm is not None:
+        chk_spp = 2
+        render(0, chk_spp)
+        r.reduce_film(comm, 0)
+        r.sync()
+        dist.barrier()
+        if rank == 0:
+            reduced = r.download_reduced_film()
+            r.film_clear()
+            r.render_pass(chk_spp, frame_count=0)
+            alone = r.download_film()
+            err = np.abs(reduced.astype(np.float64) - alone.astype(np.float64))
+            scale = np.abs(alone.astype(np.float64)) + 1e-3 * float(np.mean(np.abs(alone)))
+            multi_gpu_check = {"what": f"{world}-rank reduced film vs rank 0 rendering the full frame alone, {chk_spp} spp",
+                               "max_rel_err": float(np.max(err / scale)),
+                               "ok": bool(np.allclose(reduced, alone, rtol=1e-4, atol=1e-5))}
+        dist.barrier()
+        r.film_clear()
+        r.sync()
 
     # --- counting pass (untimed): reference-unit visit counts for the roofline, rays per pass ---
     r.stats_enable(True)
@@ -228,11 +287,12 @@ def main():
     r.sync()
     st_counts = r.get_stats(reset=True)
     r.stats_enable(False)
-    film.zero_()
+    r.film_clear()
 
     for i in range(args.warmup):
         step(i * spp)
-    film.zero_()
+    r.film_clear()
+    r.sync()
     torch.cuda.synchronize()
     if dist is not None:
         dist.barrier()
@@ -288,10 +348,13 @@ def main():
         t0 = time.perf_counter()
         for i in range(max(1, min(args.steps, 3))):
             r2.upload_scene(scene)
-            film.zero_()
+            r2.film_clear()
             step(0)
             if rank == 0:
-                r2.download_film(host_film)
+                if comm is not None:
+                    r2.download_reduced_film(host_film)
+                else:
+                    r2.download_film(host_film)
         torch.cuda.synchronize()
         if dist is not None:
             dist.barrier()
@@ -339,22 +402,19 @@ def main():
         roofline["traffic_source"] = tf.get("source")
 
     rps = rays_all / samples_all
-    os.makedirs(os.path.join(ROOT, "profiles"), exist_ok=True)
-    try:
-        with open(os.path.join(ROOT, "profiles", f"rays_per_sample_{args.config}.json"), "w") as f:
-            json.dump({"rays_per_sample": rps, "config": args.config}, f)
-    except OSError:
-        pass
 
     cpu_baseline = None
     if world == 1 and not args.no_cpu_baseline:
         try:
-            info = cpu_reference_run(args.config, w, h, seconds_target=15.0)
-            cpu_baseline = {"value": info["samples_per_s"] * rps / 1e6, "unit": "Mrays/s", "cores": info["threads"],
-                            "kind": "reference", "samples_per_s": info["samples_per_s"],
+            ref = reference_scene(args.config, w, h)
+            ref_rps, ref_rps_n = reference_rays_per_sample(ref, w, h, spp)
+            info = cpu_reference_run(args.config, w, h, seconds_target=15.0, ref=ref)
+            cpu_baseline = {"value": info["samples_per_s"] * ref_rps / 1e6, "unit": "Mrays/s", "cores": info["threads"],
+                            "kind": "reference", "samples_per_s": info["samples_per_s"], "rays_per_sample": ref_rps,
                             "sample": f"{w}x{h} at {info['spp']} spp ({info['samples']} samples), the reference's verbatim "
                                       f"WorkQueue renderer (per-tile seeding), {info['threads']} worker threads on "
-                                      f"{info['nproc']} logical CPUs; rays = samples x GPU-counted rays/sample"}
+                                      f"{info['nproc']} logical CPUs; rays = samples x rays/sample counted by the reference "
+                                      f"itself on {ref_rps_n} samples of this frame"}
         except Exception as e:  # the oracle is a checker, never a dependency of the measured path
             cpu_baseline = {"value": None, "unit": "Mrays/s", "cores": 0, "kind": "reference", "sample": f"unavailable: {e}"}
 
@@ -364,6 +424,8 @@ def main():
             "samples_per_s": samples_all / (ms_per_step * 1e-3), "rays_per_step": rays_all, "rays_per_sample": rps,
             "clocks": clk, "e2e": e2e, "gpu_launches": int(launches * args.steps), "roofline": roofline,
             "cpu_baseline": cpu_baseline}
+    if multi_gpu_check is not None:
+        line["multi_gpu_check"] = multi_gpu_check
     print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()

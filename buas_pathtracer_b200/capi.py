@@ -58,6 +58,10 @@ BVH_MIDPOINT_SPLIT, BVH_SAH_BINNED, BVH_SAH_FULL = 0, 1, 2      # BVHConstructio
 BVH_NODE_DTYPE = np.dtype([("bv_p", np.float32, 3), ("bv_r", np.float32, 3), ("left_first", np.uint32),
                            ("count", np.uint16), ("split_axis", np.uint16)])
 assert BVH_NODE_DTYPE.itemsize == 32 and C.sizeof(BvhNode) == 32
+# one child of the device layout (csrc/wide_bvh.h): the node's box verbatim + a packed reference
+WIDE_CHILD_DTYPE = np.dtype([("bv_p", np.float32, 3), ("bv_r", np.float32, 3), ("ref", np.uint32), ("aux", np.uint32)])
+assert WIDE_CHILD_DTYPE.itemsize == 32
+WREF_LEAF, WREF_RECORD_ROOT, WREF_INDEX_MASK = 0x80000000, 0x10000000, 0x0FFFFFFF
 
 
 class FilterCache(C.Structure):

@@ -2,6 +2,7 @@
 // schedule, diagnostics.  There is no CPU fallback anywhere in this file: without a usable CUDA device every entry
 // point fails with BPT_ERR_CUDA.
 #include <cuda_runtime.h>
+#include <dlfcn.h>
 #include <math.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -20,8 +21,9 @@ using namespace bpt;
 
 namespace {
 
-enum SceneSlot { SL_MATERIALS, SL_PRIMITIVES, SL_PLANES, SL_MESHES, SL_LIGHTS, SL_TLAS_NODES, SL_TLAS_INDICES, SL_BLAS_NODES,
-                 SL_TRIANGLES, SL_TRI_ORIGINAL, SL_RAW_TRIANGLES, SL_NORMALS, SL_RAW_NORMALS, SL_SKYDOME, SL_RAW_SKYDOME };
+enum SceneSlot { SL_MATERIALS, SL_PRIMITIVES, SL_PLANES, SL_MESHES, SL_LIGHTS, SL_PAIRS, SL_TLAS_INDICES, SL_BIG_LEAVES,
+                 SL_TRIANGLES, SL_TRI_ORIGINAL, SL_RAW_TRIANGLES, SL_NORMALS, SL_RAW_NORMALS, SL_SKYDOME, SL_RAW_SKYDOME,
+                 SL_TRACE_RAYS, SL_TRACE_HITS, SL_TRACE_CURSOR, SL_RESOLVE_OUT, SL_RESOLVE_DITHER, SL_COUNT };
 
 #define BPT_MAX_PIPES 4
 enum Stage { ST_RAYGEN, ST_TRACE, ST_SHADE, ST_SHADOW, ST_SPLAT, ST_COUNT };
@@ -41,7 +43,7 @@ struct bpt_ctx {
     bool scene_ready = false;
     bool tables_ready = false;
     std::vector<void*> scene_allocs;      // (unused, kept for destroy)
-    struct Slot { void* p = nullptr; size_t cap = 0; } slots[16];   // grow-only device buffers of the uploaded scene
+    struct Slot { void* p = nullptr; size_t cap = 0; } slots[SL_COUNT];   // grow-only device buffers of the uploaded scene
     char* staging = nullptr;              // pinned host block for the small flattened tables
     size_t staging_capacity = 0;
     uint32_t* tri_original = nullptr;     // DTriangle slot -> original triangle index (MeshBVH::indices)
@@ -49,7 +51,11 @@ struct bpt_ctx {
     uint8_t *d_perm = nullptr, *d_sobol = nullptr, *d_scramble = nullptr, *d_rank = nullptr;
     float* d_filter = nullptr;
 
+    uint32_t stack_bound = 0;             // TLAS depth + deepest BLAS of the uploaded scene: most stack entries one ray can have pending
+
     float4* film = nullptr;
+    float4* film_reduced = nullptr;       // root of a multi-GPU job: sum of all ranks' films (bpt_reduce_film)
+    uint32_t film_reduced_w = 0, film_reduced_h = 0;
     bool film_owned = false;
     uint32_t film_w = 0, film_h = 0;
 
@@ -76,6 +82,7 @@ struct bpt_ctx {
 
     DStats* d_stats = nullptr;
     bool stats_enabled = false;
+    uint32_t* h_error = nullptr;          // page-locked, device-mapped word the kernels raise (BPT_DEVERR_*), read after a sync
 
     bpt_sample_record* host_records = nullptr;
     uint64_t host_record_capacity = 0;
@@ -207,6 +214,20 @@ void latch_settings(bpt_ctx* ctx, const bpt_scene* scene) {
     memcpy(ctx->sc.ambient_light, scene->ambient_light, 12);
 }
 
+// what the kernels raised since the last check (the stream they ran on has been synchronised by the caller)
+int device_error(bpt_ctx* ctx, const char* who) {
+    uint32_t e = *(volatile uint32_t*)ctx->h_error;
+    if (e == BPT_DEVERR_NONE) return BPT_OK;
+    *ctx->h_error = BPT_DEVERR_NONE;
+    if (e == BPT_DEVERR_STACK_OVERFLOW) {
+        set_error("%s: a ray had more than %d far children pending (depth bound of this scene's BVHs: %u); the reference overruns "
+                  "its node_stack[64] on such a scene (intersection.cpp:261, :445) -- results of this call are incomplete", who, BPT_STACK_DEPTH, ctx->stack_bound);
+        return BPT_ERR_UNSUPPORTED;
+    }
+    set_error("%s: a traversal warp exceeded its scheduling trip limit (device error %u); results of this call are incomplete", who, e);
+    return BPT_ERR_CUDA;
+}
+
 } // namespace
 
 extern "C" {
@@ -223,6 +244,7 @@ int bpt_create(int device, bpt_ctx** out_ctx) {
     if (device < 0 || device >= count) { set_error("bpt_create: device %d out of range (0..%d)", device, count - 1); return BPT_ERR_ARG; }
     CK(cudaSetDevice(device));
     bpt_ctx* ctx = new bpt_ctx();
+    struct Guard { bpt_ctx* c; ~Guard() { if (c) bpt_destroy(c); } } guard{ctx};      // a failing CK() below releases what exists so far
     ctx->device = device;
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, device));
@@ -235,6 +257,9 @@ int bpt_create(int device, bpt_ctx** out_ctx) {
     CK(cudaMalloc((void**)&ctx->d_stats, sizeof(DStats)));
     CK(cudaMemset(ctx->d_stats, 0, sizeof(DStats)));
     CK(cudaMalloc((void**)&ctx->d_filter, 512*sizeof(float)));
+    CK(cudaHostAlloc((void**)&ctx->h_error, 64, cudaHostAllocMapped));
+    *ctx->h_error = BPT_DEVERR_NONE;
+    CK(cudaHostGetDevicePointer((void**)&ctx->sc.error_flag, ctx->h_error, 0));
     CK(cudaEventCreate(&ctx->pass_begin));
     CK(cudaEventCreate(&ctx->pass_end));
     {
@@ -254,6 +279,7 @@ int bpt_create(int device, bpt_ctx** out_ctx) {
     if (const char* e = getenv("BPT_TRACE_CTAS")) { int v = atoi(e); if (v >= 1 && v <= 32) ctx->trace_ctas_per_sm = v; }
     const char* dt = getenv("BPT_DETAILED_TIMING");
     ctx->detailed_timing = dt && atoi(dt) != 0;
+    guard.c = nullptr;
     *out_ctx = ctx;
     return BPT_OK;
 }
@@ -274,7 +300,9 @@ void bpt_destroy(bpt_ctx* ctx) {
     }
     cudaFree(ctx->d_row_map);
     if (ctx->film_owned && ctx->film) cudaFree(ctx->film);
+    cudaFree(ctx->film_reduced);
     cudaFree(ctx->d_stats); cudaFree(ctx->d_filter);
+    if (ctx->h_error) cudaFreeHost(ctx->h_error);
     cudaFree(ctx->d_perm); cudaFree(ctx->d_sobol); cudaFree(ctx->d_scramble); cudaFree(ctx->d_rank);
     for (auto& s : ctx->spans) { cudaEventDestroy(s.a); cudaEventDestroy(s.b); }
     cudaEventDestroy(ctx->pass_begin); cudaEventDestroy(ctx->pass_end);
@@ -370,22 +398,33 @@ int bpt_upload_scene(bpt_ctx* ctx, const bpt_scene* scene) {
         planes[i].material = scene->planes[i].material;
     }
 
-    // mesh directory + totals; FMNMX slab-test precondition (trace.cuh make_ray): all node boxes inside 1e15
-    size_t total_nodes = 0, total_tris = 0;
+    // mesh directory + totals; FMNMX slab-test precondition (trace.cuh make_ray): all node boxes inside 1e15.
+    // The traversal stack holds at most one pending far child per level of descent: TLAS depth + deepest BLAS.
+    if (!scene->tlas.wide.valid) { set_error("bpt_upload_scene: the scene BVH has no device layout (bpt_create_scene_bvh failed?)"); return BPT_ERR_STATE; }
+    size_t total_pairs = scene->tlas.wide.pairs.size(), total_big = scene->tlas.wide.big_leaves.size(), total_tris = 0;
+    uint32_t deepest_blas = 0;
     bool any_normals = false;
     bool tame = scene->tlas.max_abs_extent < 1e15f || scene->tlas.indices.empty();
     for (size_t mi = 0; mi < n_meshes; ++mi) {
         const HostMesh& m = scene->meshes[mi];
-        meshes[mi].node_base = (uint32_t)total_nodes;
+        if (!m.bvh.wide.valid) { set_error("bpt_upload_scene: mesh %zu has no device BVH layout", mi); return BPT_ERR_STATE; }
+        memcpy(&meshes[mi].root_q0, &m.bvh.wide.root, sizeof(WChild));
+        meshes[mi].pair_base = (uint32_t)total_pairs;
         meshes[mi].tri_base = (uint32_t)total_tris;
         meshes[mi].triangle_count = m.triangle_count;
         meshes[mi].has_normals = m.has_normals ? 1u : 0u;
-        total_nodes += (m.bvh.nodes.size() + 1) & ~(size_t)1;      // keep sibling pairs 64-byte aligned
+        meshes[mi].big_base = (uint32_t)total_big;
+        total_pairs += m.bvh.wide.pairs.size();
+        total_big += m.bvh.wide.big_leaves.size();
         total_tris += m.triangle_count;
         any_normals |= m.has_normals;
         tame = tame && (m.bvh.max_abs_extent < 1e15f);
+        deepest_blas = std::max(deepest_blas, m.bvh.wide.depth);
     }
+    if (total_pairs > 0x7FFFFFFFull || total_tris > 0x7FFFFFFFull) { set_error("bpt_upload_scene: scene too large for 32-bit pair / triangle indices"); return BPT_ERR_UNSUPPORTED; }
+    ctx->stack_bound = scene->tlas.wide.depth + deepest_blas;
     sc.tame_bounds = tame ? 1u : 0u;
+    memcpy(&sc.tlas_root_q0, &scene->tlas.wide.root, sizeof(WChild));
 
     void* d = nullptr;
     #define SLOT(id, bytes) do { int rc_ = device_slot(ctx, id, (bytes), &d); if (rc_) return rc_; } while (0)
@@ -395,12 +434,12 @@ int bpt_upload_scene(bpt_ctx* ctx, const bpt_scene* scene) {
     SLOT(SL_PLANES, n_planes*sizeof(DPlane));       sc.planes = (const DPlane*)d;         H2D(d, planes, n_planes*sizeof(DPlane));
     SLOT(SL_MESHES, n_meshes*sizeof(DMesh));        sc.meshes = (const DMesh*)d;          H2D(d, meshes, n_meshes*sizeof(DMesh));
     SLOT(SL_LIGHTS, n_lights*sizeof(uint32_t));     sc.lights = (const uint32_t*)d;       H2D(d, scene->lights.data(), n_lights*sizeof(uint32_t));
-    SLOT(SL_TLAS_NODES, scene->tlas.nodes.size()*sizeof(bpt_bvh_node)); sc.tlas_nodes = (const DNodeHalf*)d;
-    H2D(d, scene->tlas.nodes.data(), scene->tlas.nodes.size()*sizeof(bpt_bvh_node));
     SLOT(SL_TLAS_INDICES, scene->tlas.indices.size()*sizeof(uint32_t)); sc.tlas_indices = (const uint32_t*)d;
     H2D(d, scene->tlas.indices.data(), scene->tlas.indices.size()*sizeof(uint32_t));
 
-    SLOT(SL_BLAS_NODES, total_nodes*sizeof(bpt_bvh_node)); bpt_bvh_node* d_blas = (bpt_bvh_node*)d; sc.blas_nodes = (const DNodeHalf*)d;
+    // pair records: the TLAS's first (its refs are relative to pair 0), then every BLAS's at its pair_base
+    SLOT(SL_PAIRS, total_pairs*sizeof(DPair));             DPair* d_pairs = (DPair*)d;              sc.pairs = d_pairs;
+    SLOT(SL_BIG_LEAVES, total_big*sizeof(uint2));          uint2* d_big = (uint2*)d;                sc.big_leaves = d_big;
     SLOT(SL_TRIANGLES, total_tris*sizeof(DTriangle));      DTriangle* d_tris = (DTriangle*)d;       sc.triangles = d_tris;
     SLOT(SL_TRI_ORIGINAL, total_tris*sizeof(uint32_t));    uint32_t* d_orig = (uint32_t*)d;         ctx->tri_original = d_orig;
     SLOT(SL_RAW_TRIANGLES, total_tris*9*sizeof(float));    float* d_raw = (float*)d;
@@ -410,11 +449,13 @@ int bpt_upload_scene(bpt_ctx* ctx, const bpt_scene* scene) {
         SLOT(SL_NORMALS, total_tris*3*sizeof(float4));     d_normals = (float4*)d; sc.normals = d_normals;
         SLOT(SL_RAW_NORMALS, total_tris*9*sizeof(float));  d_raw_normals = (float*)d;
     }
+    H2D(d_pairs, scene->tlas.wide.pairs.data(), scene->tlas.wide.pairs.size()*sizeof(WPair));
+    H2D(d_big, scene->tlas.wide.big_leaves.data(), scene->tlas.wide.big_leaves.size()*sizeof(WBigLeaf));
     for (size_t mi = 0; mi < n_meshes; ++mi) {
         const HostMesh& m = scene->meshes[mi];
-        size_t nb = meshes[mi].node_base, tb = meshes[mi].tri_base, nt = m.triangle_count;
-        H2D(d_blas + nb, m.bvh.nodes.data(), m.bvh.nodes.size()*sizeof(bpt_bvh_node));
-        if (m.bvh.nodes.size() & 1) CK(cudaMemsetAsync(d_blas + nb + m.bvh.nodes.size(), 0, sizeof(bpt_bvh_node), s));
+        size_t pb = meshes[mi].pair_base, tb = meshes[mi].tri_base, bb = meshes[mi].big_base, nt = m.triangle_count;
+        H2D(d_pairs + pb, m.bvh.wide.pairs.data(), m.bvh.wide.pairs.size()*sizeof(WPair));
+        H2D(d_big + bb, m.bvh.wide.big_leaves.data(), m.bvh.wide.big_leaves.size()*sizeof(WBigLeaf));
         H2D(d_raw + tb*9, m.leaf_triangles.data(), nt*9*sizeof(float));
         H2D(d_orig + tb, m.bvh.indices.data(), nt*sizeof(uint32_t));
         if (m.has_normals) H2D(d_raw_normals + tb*9, m.normals.data(), nt*9*sizeof(float));
@@ -495,7 +536,7 @@ int bpt_download_film(bpt_ctx* ctx, float* out) {
     CK(cudaMemcpyAsync(out, ctx->film, (size_t)ctx->film_w*ctx->film_h*sizeof(float4), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     ctx->d2h_bytes += (uint64_t)ctx->film_w*ctx->film_h*sizeof(float4);
-    return BPT_OK;
+    return device_error(ctx, "bpt_download_film");
 }
 
 int bpt_sync(bpt_ctx* ctx) {
@@ -503,7 +544,7 @@ int bpt_sync(bpt_ctx* ctx) {
     CK(cudaSetDevice(ctx->device));
     CK(cudaStreamSynchronize(ctx->stream));
     CK(cudaGetLastError());
-    return BPT_OK;
+    return device_error(ctx, "bpt_sync");
 }
 
 int bpt_stats_enable(bpt_ctx* ctx, int enable) {
@@ -542,30 +583,28 @@ int bpt_trace(bpt_ctx* ctx, uint32_t n, const bpt_ray* rays, int mode, uint32_t 
     if (mode != BPT_TRACE_CLOSEST && mode != BPT_TRACE_OCCLUSION) { set_error("bpt_trace: bad mode"); return BPT_ERR_ARG; }
     if (n == 0) return BPT_OK;
     CK(cudaSetDevice(ctx->device));
-    bpt_ray* d_rays = nullptr; bpt_hit* d_hits = nullptr;
-    CK(cudaMalloc((void**)&d_rays, (size_t)n*sizeof(bpt_ray)));
-    CK(cudaMalloc((void**)&d_hits, (size_t)n*sizeof(bpt_hit)));
+    // grow-only device buffers owned by the context (no allocation per call, nothing to leak on an error path)
+    void* d = nullptr;
+    int rc = device_slot(ctx, SL_TRACE_RAYS, (size_t)n*sizeof(bpt_ray), &d);   if (rc) return rc;  bpt_ray* d_rays = (bpt_ray*)d;
+    rc = device_slot(ctx, SL_TRACE_HITS, (size_t)n*sizeof(bpt_hit), &d);       if (rc) return rc;  bpt_hit* d_hits = (bpt_hit*)d;
+    rc = device_slot(ctx, SL_TRACE_CURSOR, 256, &d);                           if (rc) return rc;  uint32_t* d_cursor = (uint32_t*)d;
     CK(cudaMemcpyAsync(d_rays, rays, (size_t)n*sizeof(bpt_ray), cudaMemcpyHostToDevice, ctx->stream));
     ctx->h2d_bytes += (uint64_t)n*sizeof(bpt_ray); ctx->d2h_bytes += (uint64_t)n*sizeof(bpt_hit);
-    uint32_t* d_cursor = nullptr;
-    CK(cudaMalloc((void**)&d_cursor, 256));
     CK(cudaMemsetAsync(d_cursor, 0, 256, ctx->stream));
-    uint32_t grid = grid_for(ctx, n, 128, ctx->trace_ctas_per_sm);
+    uint32_t grid = grid_for(ctx, n, BPT_TRACE_THREADS, ctx->trace_ctas_per_sm);
     bool st = ctx->stats_enabled;
     if (mode == BPT_TRACE_CLOSEST) {
-        if (st) k_trace_api<false, true ><<<grid, 128, 0, ctx->stream>>>(ctx->sc, d_rays, n, ignored, d_hits, ctx->tri_original, d_cursor, ctx->refill, ctx->d_stats);
-        else    k_trace_api<false, false><<<grid, 128, 0, ctx->stream>>>(ctx->sc, d_rays, n, ignored, d_hits, ctx->tri_original, d_cursor, ctx->refill, ctx->d_stats);
+        if (st) k_trace_api<false, true ><<<grid, BPT_TRACE_THREADS, 0, ctx->stream>>>(ctx->sc, d_rays, n, ignored, d_hits, ctx->tri_original, d_cursor, ctx->refill, ctx->d_stats);
+        else    k_trace_api<false, false><<<grid, BPT_TRACE_THREADS, 0, ctx->stream>>>(ctx->sc, d_rays, n, ignored, d_hits, ctx->tri_original, d_cursor, ctx->refill, ctx->d_stats);
     } else {
-        if (st) k_trace_api<true, true ><<<grid, 128, 0, ctx->stream>>>(ctx->sc, d_rays, n, ignored, d_hits, ctx->tri_original, d_cursor, ctx->refill, ctx->d_stats);
-        else    k_trace_api<true, false><<<grid, 128, 0, ctx->stream>>>(ctx->sc, d_rays, n, ignored, d_hits, ctx->tri_original, d_cursor, ctx->refill, ctx->d_stats);
+        if (st) k_trace_api<true, true ><<<grid, BPT_TRACE_THREADS, 0, ctx->stream>>>(ctx->sc, d_rays, n, ignored, d_hits, ctx->tri_original, d_cursor, ctx->refill, ctx->d_stats);
+        else    k_trace_api<true, false><<<grid, BPT_TRACE_THREADS, 0, ctx->stream>>>(ctx->sc, d_rays, n, ignored, d_hits, ctx->tri_original, d_cursor, ctx->refill, ctx->d_stats);
     }
     ctx->total_launches += 1;
-    cudaError_t e = cudaGetLastError();
-    if (e == cudaSuccess) e = cudaMemcpyAsync(out, d_hits, (size_t)n*sizeof(bpt_hit), cudaMemcpyDeviceToHost, ctx->stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-    cudaFree(d_rays); cudaFree(d_hits); cudaFree(d_cursor);
-    if (e != cudaSuccess) { set_error("bpt_trace: %s", cudaGetErrorString(e)); return BPT_ERR_CUDA; }
-    return BPT_OK;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(out, d_hits, (size_t)n*sizeof(bpt_hit), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return device_error(ctx, "bpt_trace");
 }
 
 static int render_rows(bpt_ctx* ctx, int32_t x0, int32_t x1, const std::vector<int32_t>& rows,
@@ -597,7 +636,9 @@ static int render_rows(bpt_ctx* ctx, int32_t x0, int32_t x1, const std::vector<i
     if (const char* e = getenv("BPT_MAX_SLOTS")) { uint64_t v = strtoull(e, nullptr, 10); if (v >= 1024) cap = v; }
     uint32_t S, rows_per_batch;
     uint64_t n_batches;
+    const int n_pipes_wanted = n_pipes;
 retry_shape:
+    n_pipes = n_pipes_wanted;             // a retry changes the batch count, and with it how many pipelines can be fed
     S = (uint32_t)std::min<uint64_t>(spp, std::max<uint64_t>(1, cap / rect_w));
     rows_per_batch = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(rect_h, cap / ((uint64_t)rect_w*S)));
     n_batches = (uint64_t)((spp + S - 1)/S) * ((rect_h + rows_per_batch - 1)/rows_per_batch);
@@ -832,32 +873,45 @@ int bpt_get_pass_timing(bpt_ctx* ctx, bpt_pass_timing* out) {
     return BPT_OK;
 }
 
+static int resolve_film(bpt_ctx* ctx, const float4* film, const bpt_post_settings* post, const uint8_t* dither_rgb8,
+                        uint32_t dither_w, uint32_t dither_h, uint32_t* out_pixels, const char* who) {
+    if (dither_rgb8 && (dither_w == 0 || dither_h == 0 || (dither_w & (dither_w - 1)) || (dither_h & (dither_h - 1)))) {
+        set_error("%s: dither tile must have power-of-two width and height", who); return BPT_ERR_ARG;
+    }
+    CK(cudaSetDevice(ctx->device));
+    size_t n = (size_t)ctx->film_w*ctx->film_h;
+    void* d = nullptr;
+    int rc = device_slot(ctx, SL_RESOLVE_OUT, n*sizeof(uint32_t), &d);   if (rc) return rc;   uint32_t* d_out = (uint32_t*)d;
+    uint8_t* d_dither = nullptr;
+    if (dither_rgb8) {
+        size_t db = (size_t)dither_w*dither_h*3;
+        rc = device_slot(ctx, SL_RESOLVE_DITHER, db, &d);   if (rc) return rc;   d_dither = (uint8_t*)d;
+        CK(cudaMemcpyAsync(d_dither, dither_rgb8, db, cudaMemcpyHostToDevice, ctx->stream));
+        ctx->h2d_bytes += db;
+    }
+    k_resolve<<<grid_for(ctx, n, 256, 8), 256, 0, ctx->stream>>>(film, ctx->film_w, ctx->film_h, *post, d_dither, dither_w, dither_h, d_out);
+    ctx->total_launches += 1;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(out_pixels, d_out, n*sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->d2h_bytes += n*sizeof(uint32_t);
+    return device_error(ctx, who);
+}
+
 int bpt_resolve_bgra8(bpt_ctx* ctx, const bpt_post_settings* post, const uint8_t* dither_rgb8,
                       uint32_t dither_w, uint32_t dither_h, uint32_t* out_pixels) {
     if (!ctx || !post || !out_pixels) { set_error("bpt_resolve_bgra8: null argument"); return BPT_ERR_ARG; }
     if (!ctx->film) { set_error("bpt_resolve_bgra8: no film"); return BPT_ERR_STATE; }
-    if (dither_rgb8 && (dither_w == 0 || dither_h == 0 || (dither_w & (dither_w - 1)) || (dither_h & (dither_h - 1)))) {
-        set_error("bpt_resolve_bgra8: dither tile must have power-of-two width and height"); return BPT_ERR_ARG;
+    return resolve_film(ctx, ctx->film, post, dither_rgb8, dither_w, dither_h, out_pixels, "bpt_resolve_bgra8");
+}
+
+int bpt_resolve_reduced_bgra8(bpt_ctx* ctx, const bpt_post_settings* post, const uint8_t* dither_rgb8,
+                              uint32_t dither_w, uint32_t dither_h, uint32_t* out_pixels) {
+    if (!ctx || !post || !out_pixels) { set_error("bpt_resolve_reduced_bgra8: null argument"); return BPT_ERR_ARG; }
+    if (!ctx->film_reduced || ctx->film_reduced_w != ctx->film_w || ctx->film_reduced_h != ctx->film_h) {
+        set_error("bpt_resolve_reduced_bgra8: bpt_reduce_film has not run for this film"); return BPT_ERR_STATE;
     }
-    CK(cudaSetDevice(ctx->device));
-    size_t n = (size_t)ctx->film_w*ctx->film_h;
-    uint32_t* d_out = nullptr; uint8_t* d_dither = nullptr;
-    CK(cudaMalloc((void**)&d_out, n*sizeof(uint32_t)));
-    if (dither_rgb8) {
-        size_t db = (size_t)dither_w*dither_h*3;
-        if (cudaMalloc((void**)&d_dither, db) != cudaSuccess) { cudaFree(d_out); set_error("bpt_resolve_bgra8: out of memory"); return BPT_ERR_CUDA; }
-        cudaMemcpyAsync(d_dither, dither_rgb8, db, cudaMemcpyHostToDevice, ctx->stream);
-        ctx->h2d_bytes += db;
-    }
-    k_resolve<<<grid_for(ctx, n, 256, 8), 256, 0, ctx->stream>>>(ctx->film, ctx->film_w, ctx->film_h, *post, d_dither, dither_w, dither_h, d_out);
-    ctx->total_launches += 1;
-    cudaError_t e = cudaGetLastError();
-    if (e == cudaSuccess) e = cudaMemcpyAsync(out_pixels, d_out, n*sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-    cudaFree(d_out); cudaFree(d_dither);
-    if (e != cudaSuccess) { set_error("bpt_resolve_bgra8: %s", cudaGetErrorString(e)); return BPT_ERR_CUDA; }
-    ctx->d2h_bytes += n*sizeof(uint32_t);
-    return BPT_OK;
+    return resolve_film(ctx, ctx->film_reduced, post, dither_rgb8, dither_w, dither_h, out_pixels, "bpt_resolve_reduced_bgra8");
 }
 
 int bpt_build_mesh_bvh_device(bpt_ctx* ctx, uint32_t n, const float* positions, int32_t method, bpt_bvh_node* nodes_out,
@@ -971,6 +1025,103 @@ int bpt_build_mesh_bvh_device(bpt_ctx* ctx, uint32_t n, const float* positions, 
     *node_count = out_count;
     if (build_ms) *build_ms = ms;
     return BPT_OK;
+}
+
+// ---- multi-GPU: NCCL is resolved at run time so that single-GPU users of the library do not need it ------------------------
+namespace {
+struct NcclApi {
+    void* handle = nullptr;
+    int (*GetUniqueId)(void*) = nullptr;
+    int (*CommInitRank)(void**, int, bpt_nccl_id, int) = nullptr;     // ncclUniqueId is passed by value: same 128-byte POD
+    int (*CommInitAll)(void**, int, const int*) = nullptr;
+    int (*CommDestroy)(void*) = nullptr;
+    int (*Reduce)(const void*, void*, size_t, int, int, int, void*, cudaStream_t) = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+    bool ok = false;
+};
+NcclApi* nccl_api() {
+    static NcclApi api;
+    static bool tried = false;
+    if (tried) return api.ok ? &api : nullptr;
+    tried = true;
+    const char* names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char* nm : names) { api.handle = dlopen(nm, RTLD_NOW | RTLD_GLOBAL); if (api.handle) break; }
+    if (!api.handle) { set_error("multi-GPU: cannot load libnccl.so.2 (%s)", dlerror()); return nullptr; }
+    #define SYM(field, name) do { *(void**)&api.field = dlsym(api.handle, name); if (!api.field) { set_error("multi-GPU: %s missing from libnccl", name); return nullptr; } } while (0)
+    SYM(GetUniqueId, "ncclGetUniqueId"); SYM(CommInitRank, "ncclCommInitRank"); SYM(CommInitAll, "ncclCommInitAll");
+    SYM(CommDestroy, "ncclCommDestroy"); SYM(Reduce, "ncclReduce"); SYM(GetErrorString, "ncclGetErrorString");
+    #undef SYM
+    api.ok = true;
+    return &api;
+}
+enum { kNcclFloat32 = 7, kNcclSum = 0 };        // ncclFloat32 / ncclSum (nccl.h: ncclDataType_t, ncclRedOp_t)
+#define NK(api, call, what) do { int r_ = (call); if (r_ != 0) { set_error("%s: NCCL error %d (%s)", what, r_, (api)->GetErrorString(r_)); return BPT_ERR_CUDA; } } while (0)
+} // namespace
+
+int bpt_nccl_get_unique_id(bpt_nccl_id* out) {
+    if (!out) { set_error("bpt_nccl_get_unique_id: null argument"); return BPT_ERR_ARG; }
+    NcclApi* api = nccl_api(); if (!api) return BPT_ERR_UNSUPPORTED;
+    NK(api, api->GetUniqueId(out), "ncclGetUniqueId");
+    return BPT_OK;
+}
+
+int bpt_nccl_comm_init_rank(bpt_ctx* ctx, const bpt_nccl_id* id, int nranks, int rank, void** out_comm) {
+    if (!ctx || !id || !out_comm || nranks < 1 || rank < 0 || rank >= nranks) { set_error("bpt_nccl_comm_init_rank: bad arguments"); return BPT_ERR_ARG; }
+    NcclApi* api = nccl_api(); if (!api) return BPT_ERR_UNSUPPORTED;
+    CK(cudaSetDevice(ctx->device));
+    NK(api, api->CommInitRank(out_comm, nranks, *id, rank), "ncclCommInitRank");
+    return BPT_OK;
+}
+
+int bpt_nccl_comm_init_all(int ndev, const int* devices, void** out_comms) {
+    if (ndev < 1 || !out_comms) { set_error("bpt_nccl_comm_init_all: bad arguments"); return BPT_ERR_ARG; }
+    NcclApi* api = nccl_api(); if (!api) return BPT_ERR_UNSUPPORTED;
+    NK(api, api->CommInitAll(out_comms, ndev, devices), "ncclCommInitAll");
+    return BPT_OK;
+}
+
+int bpt_nccl_comm_destroy(void* comm) {
+    if (!comm) return BPT_OK;
+    NcclApi* api = nccl_api(); if (!api) return BPT_ERR_UNSUPPORTED;
+    NK(api, api->CommDestroy(comm), "ncclCommDestroy");
+    return BPT_OK;
+}
+
+int bpt_reduce_film(bpt_ctx* ctx, void* nccl_comm, int root) {
+    if (!ctx || !nccl_comm || root < 0) { set_error("bpt_reduce_film: bad arguments"); return BPT_ERR_ARG; }
+    if (!ctx->film) { set_error("bpt_reduce_film: no film"); return BPT_ERR_STATE; }
+    NcclApi* api = nccl_api(); if (!api) return BPT_ERR_UNSUPPORTED;
+    CK(cudaSetDevice(ctx->device));
+    size_t count = (size_t)ctx->film_w*ctx->film_h*4;
+    // every rank owns a destination buffer (NCCL only writes the root's): the caller does not have to know its rank here
+    if (!ctx->film_reduced || ctx->film_reduced_w != ctx->film_w || ctx->film_reduced_h != ctx->film_h) {
+        CK(cudaStreamSynchronize(ctx->stream));
+        cudaFree(ctx->film_reduced); ctx->film_reduced = nullptr;
+        CK(cudaMalloc((void**)&ctx->film_reduced, count*sizeof(float)));
+        CK(cudaMemsetAsync(ctx->film_reduced, 0, count*sizeof(float), ctx->stream));
+        ctx->film_reduced_w = ctx->film_w; ctx->film_reduced_h = ctx->film_h;
+    }
+    // on the context's stream: behind every pass enqueued so far (render_rows joins its pipeline streams into it), and
+    // the next pass starts behind it -- no host synchronisation anywhere
+    NK(api, api->Reduce(ctx->film, ctx->film_reduced, count, kNcclFloat32, kNcclSum, root, nccl_comm, ctx->stream), "ncclReduce");
+    return BPT_OK;
+}
+
+int bpt_reduced_film_device_ptr(bpt_ctx* ctx, void** out) {
+    if (!ctx || !out) { set_error("bpt_reduced_film_device_ptr: null argument"); return BPT_ERR_ARG; }
+    *out = ctx->film_reduced;
+    return ctx->film_reduced ? BPT_OK : BPT_ERR_STATE;
+}
+
+int bpt_download_reduced_film(bpt_ctx* ctx, float* out) {
+    if (!ctx || !out) { set_error("bpt_download_reduced_film: null argument"); return BPT_ERR_ARG; }
+    if (!ctx->film_reduced) { set_error("bpt_download_reduced_film: bpt_reduce_film has not run"); return BPT_ERR_STATE; }
+    CK(cudaSetDevice(ctx->device));
+    size_t bytes = (size_t)ctx->film_reduced_w*ctx->film_reduced_h*sizeof(float4);
+    CK(cudaMemcpyAsync(out, ctx->film_reduced, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->d2h_bytes += bytes;
+    return device_error(ctx, "bpt_download_reduced_film");
 }
 
 int bpt_set_tail_threshold(bpt_ctx* ctx, uint32_t paths) {

@@ -253,6 +253,7 @@ void build_bvh(std::vector<SortEntry>& entries, HostBVH* out, int method) {
     out->max_abs_extent = ext;
     out->indices.resize(n);
     for (uint32_t i = 0; i < n; ++i) out->indices[i] = entries[i].index;
+    build_wide_bvh(out, n);              // the device layout of the same tree (cannot fail for a tree built here)
 }
 
 void build_mesh_bvh(HostMesh* mesh) { build_mesh_bvh(mesh, BPT_BVH_SAH_BINNED); }

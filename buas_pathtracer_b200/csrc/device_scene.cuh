@@ -4,26 +4,34 @@
 #include <cuda_runtime.h>
 
 #include "../../include/bpt.h"
+#include "wide_bvh.h"
 
 namespace bpt {
 
+// raised by kernels in DScene::error_flag, reported by the next synchronising entry point
+enum { BPT_DEVERR_NONE = 0, BPT_DEVERR_STACK_OVERFLOW = 1, BPT_DEVERR_TRIP_LIMIT = 2 };
+
 // ---- acceleration structures -------------------------------------------------------------------------------------
-// Node pairs: the reference allocates BVH children pairwise at even indices (bvh.cpp:259-260, :302-303), so
-// nodes[2k], nodes[2k+1] already form one 64-byte sibling record.  On the device the array is 128-byte aligned
-// and a sibling pair is fetched with four 128-bit loads; pair 0 is {root, zero pad}.  Word layout per node:
-//   q0 = {bv_p.x, bv_p.y, bv_p.z, bv_r.x}   q1 = {bv_r.y, bv_r.z, left_first, count | split_axis << 16}
-struct DNodeHalf { float4 q0; float4 q1; };
+// Two-level pair records (wide_bvh.h): the reference's binary BVH re-laid-out on the host.  A child is two 128-bit
+// words, a sibling pair four, a record (pair of X, pair of X's child 0, pair of X's child 1) twelve:
+//   q0 = {bv_p.x, bv_p.y, bv_p.z, bv_r.x}   q1 = {bv_r.y, bv_r.z, ref, aux}
+struct DChild { float4 q0; float4 q1; };
+struct DPair { DChild c[2]; };
+static_assert(sizeof(DChild) == sizeof(WChild) && sizeof(DPair) == sizeof(WPair), "device / host layouts of the pair records differ");
 
 // Leaf triangles, leaf order, 48 bytes = 3 x 128-bit:  {a.xyz, original index}  {b-a, 0}  {c-a, 0}.
 // b-a / c-a are the first two operations of ray_intersect_triangle (intersection.cpp:145-146); hoisting them to
 // upload time is exact (same IEEE subtraction, once instead of per test).
 struct DTriangle { float4 a_idx; float4 e1; float4 e2; };
 
-struct DMesh {
-    uint32_t node_base;        // index of this BLAS's node 0 in DScene::blas_nodes
+struct DMesh {                 // 64 bytes
+    float4   root_q0, root_q1; // the BLAS root as a child record: box + ref
+    uint32_t pair_base;        // index of this BLAS's pair 0 in DScene::pairs
     uint32_t tri_base;         // index of its first DTriangle in DScene::triangles (also indexes normals)
     uint32_t triangle_count;
     uint32_t has_normals;
+    uint32_t big_base;         // its first entry in DScene::big_leaves
+    uint32_t pad[3];
 };
 
 // Primitive (primitives.h:92-106) flattened; rows 0..2 of the inverse / forward matrices (row 3 is never read
@@ -53,9 +61,11 @@ struct DMaterial {             // Material (scene.h:15-29) + padding to 80 bytes
 };
 
 struct DScene {
-    const DNodeHalf*  tlas_nodes;
+    const DPair*      pairs;           // TLAS pairs (from index 0) then every BLAS's pairs, back to back
+    const uint2*      big_leaves;      // {first, count} of leaves with more than 7 items; TLAS entries first
     const uint32_t*   tlas_indices;
-    const DNodeHalf*  blas_nodes;      // all BLASes back to back
+    float4            tlas_root_q0, tlas_root_q1;   // the TLAS root as a child record (in the kernel's constant bank)
+    uint32_t*         error_flag;      // device-visible word the kernels raise on an internal limit (BPT_DEVERR_*)
     const DTriangle*  triangles;       // all meshes back to back, leaf order
     const float4*     normals;         // 3 x float4 per triangle (leaf order), only for has_normals meshes; may be null
     const DMesh*      meshes;

@@ -324,6 +324,9 @@ uint32_t bpt_create_mesh_with_bvh(bpt_scene* s, uint32_t triangle_count, const f
             if (!(e <= ext)) ext = e;
         }
     m.bvh.max_abs_extent = ext;
+    // the re-layout walks the whole tree and rejects malformed node arrays (children past the array, cycles, leaf ranges
+    // past the triangles) that would otherwise make the device traversal read out of bounds or never end
+    if (build_wide_bvh(&m.bvh, triangle_count) != BPT_OK) { s->meshes.pop_back(); return 0xFFFFFFFFu; }
     m.leaf_triangles.resize((size_t)triangle_count*9);
     for (uint32_t i = 0; i < triangle_count; ++i)
         memcpy(&m.leaf_triangles[(size_t)i*9], &m.positions[(size_t)indices[i]*9], 9*sizeof(float));
@@ -429,6 +432,26 @@ int bpt_get_mesh_bvh(const bpt_scene* s, uint32_t mesh, const bpt_bvh_node** nod
     return BPT_OK;
 }
 
+int bpt_get_wide_bvh(const bpt_scene* s, int32_t mesh, const bpt_wide_child** pairs, uint32_t* pair_count,
+                     bpt_wide_child* root, const uint32_t** big_leaves, uint32_t* big_leaf_count, uint32_t* depth) {
+    static_assert(sizeof(bpt_wide_child) == sizeof(WChild) && sizeof(WBigLeaf) == 8, "wide BVH view layout");
+    if (!s || !pairs || !pair_count || !root || !big_leaves || !big_leaf_count || !depth) { set_error("bpt_get_wide_bvh: null argument"); return BPT_ERR_ARG; }
+    const HostBVH* bvh = nullptr;
+    if (mesh < 0) {
+        if (!s->has_tlas) { set_error("bpt_get_wide_bvh: call bpt_create_scene_bvh first"); return BPT_ERR_STATE; }
+        bvh = &s->tlas;
+    } else {
+        if ((size_t)mesh >= s->meshes.size()) { set_error("bpt_get_wide_bvh: unknown mesh %d", mesh); return BPT_ERR_ARG; }
+        bvh = &s->meshes[(size_t)mesh].bvh;
+    }
+    if (!bvh->wide.valid) { set_error("bpt_get_wide_bvh: no device layout was built"); return BPT_ERR_STATE; }
+    *pairs = (const bpt_wide_child*)bvh->wide.pairs.data(); *pair_count = (uint32_t)bvh->wide.pairs.size();
+    memcpy(root, &bvh->wide.root, sizeof(WChild));
+    *big_leaves = (const uint32_t*)bvh->wide.big_leaves.data(); *big_leaf_count = (uint32_t)bvh->wide.big_leaves.size();
+    *depth = bvh->wide.depth;
+    return BPT_OK;
+}
+
 int bpt_get_counts(const bpt_scene* s, uint32_t* materials, uint32_t* primitives, uint32_t* planes, uint32_t* lights, uint32_t* meshes) {
     if (materials)  *materials  = (uint32_t)s->materials.size();
     if (primitives) *primitives = (uint32_t)s->primitives.size();
@@ -459,70 +482,6 @@ int bpt_write_bitmap(const char* file_name, const uint32_t* pixels, uint32_t w, 
 
 // ---- procedural inputs for the BASELINE.json configs --------------------------------------------------------------
 
-uint32_t bpt_make_displaced_icosphere(uint32_t level, float amplitude, float* positions) {
-    if (level > 10) { set_error("icosphere level > 10"); return 0; }
-    uint32_t count = 20;
-    for (uint32_t l = 0; l < level; ++l) count *= 4;
-    if (!positions) return count;
-
-    const float t = 1.61803398875f;
-    const float V[12][3] = {{-1, t, 0}, {1, t, 0}, {-1, -t, 0}, {1, -t, 0}, {0, -1, t}, {0, 1, t},
-                            {0, -1, -t}, {0, 1, -t}, {t, 0, -1}, {t, 0, 1}, {-t, 0, -1}, {-t, 0, 1}};
-    const int F[20][3] = {{0,11,5},{0,5,1},{0,1,7},{0,7,10},{0,10,11},{1,5,9},{5,11,4},{11,10,2},{10,7,6},{7,1,8},
-                          {3,9,4},{3,4,2},{3,2,6},{3,6,8},{3,8,9},{4,9,5},{2,4,11},{6,2,10},{8,6,7},{9,8,1}};
-    std::vector<float> cur((size_t)20*9), next;
-    for (int f = 0; f < 20; ++f) for (int v = 0; v < 3; ++v) {
-        F3 p = normalize3({V[F[f][v]][0], V[F[f][v]][1], V[F[f][v]][2]});
-        st(&cur[(size_t)f*9 + v*3], p);
-    }
-    for (uint32_t l = 0; l < level; ++l) {
-        size_t n = cur.size()/9;
-        next.resize(n*4*9);
-        for (size_t i = 0; i < n; ++i) {
-            F3 a = f3(&cur[i*9]), b = f3(&cur[i*9 + 3]), c = f3(&cur[i*9 + 6]);
-            // midpoints are symmetric in their endpoints, so shared edges stay watertight
-            F3 ab = normalize3({(a.x + b.x)*0.5f, (a.y + b.y)*0.5f, (a.z + b.z)*0.5f});
-            F3 bc = normalize3({(b.x + c.x)*0.5f, (b.y + c.y)*0.5f, (b.z + c.z)*0.5f});
-            F3 ca = normalize3({(c.x + a.x)*0.5f, (c.y + a.y)*0.5f, (c.z + a.z)*0.5f});
-            F3 out[4][3] = {{a, ab, ca}, {ab, b, bc}, {ca, bc, c}, {ab, bc, ca}};
-            for (int k = 0; k < 4; ++k) for (int v = 0; v < 3; ++v) st(&next[(i*4 + k)*9 + v*3], out[k][v]);
-        }
-        cur.swap(next);
-    }
-    for (size_t i = 0; i < cur.size(); i += 3) {
-        float x = cur[i], y = cur[i + 1], z = cur[i + 2];
-        float s = 1.0f + amplitude*sinf(9.0f*x)*sinf(7.0f*y)*sinf(11.0f*z);
-        positions[i] = x*s; positions[i + 1] = y*s; positions[i + 2] = z*s;
-    }
-    return count;
-}
-
-int bpt_make_procedural_skydome(uint32_t w, uint32_t h, float* pixels) {
-    if (!pixels || w == 0 || h == 0) { set_error("bpt_make_procedural_skydome: bad arguments"); return BPT_ERR_ARG; }
-    const F3 sun = normalize3({0.45f, 0.55f, -0.70f});
-    for (uint32_t y = 0; y < h; ++y) {
-        float v = ((float)y + 0.5f) / (float)h;
-        float theta = (v - 0.5f)*kPi;                  // latitude, matches sample_sky's v = 0.5 + asin(d.y)/pi
-        float cy = cosf(theta), sy = sinf(theta);
-        for (uint32_t x = 0; x < w; ++x) {
-            float u = ((float)x + 0.5f) / (float)w;
-            float phi = (u - 0.5f)*2.0f*kPi;           // u = 0.5 + atan2(d.z, d.x)/2pi
-            F3 d = {cy*cosf(phi), sy, cy*sinf(phi)};
-            float up = d.y > 0.0f ? d.y : 0.0f;
-            float down = d.y < 0.0f ? -d.y : 0.0f;
-            float r = 0.55f*(1.0f - up) + 0.10f*up, g = 0.65f*(1.0f - up) + 0.25f*up, b = 0.80f*(1.0f - up) + 0.90f*up;
-            float gr = 1.0f - 0.75f*down;              // darker "ground" hemisphere
-            r *= gr; g *= gr*0.95f; b *= gr*0.85f;
-            float c = dot3(d, sun);
-            float halo = expf(-(1.0f - c)*60.0f)*4.0f;
-            float disc = c > 0.9995f ? 400.0f : 0.0f;  // HDR sun
-            float* px = &pixels[((size_t)y*w + x)*3];
-            px[0] = r + (halo + disc)*1.00f;
-            px[1] = g + (halo + disc)*0.92f;
-            px[2] = b + (halo + disc)*0.80f;
-        }
-    }
-    return BPT_OK;
-}
+// bpt_make_displaced_icosphere / bpt_make_procedural_skydome: procedural_inputs.cpp
 
 } // extern "C"

@@ -9,6 +9,7 @@
 #include <vector>
 
 #include "../../include/bpt.h"
+#include "wide_bvh.h"
 
 namespace bpt {
 
@@ -29,10 +30,21 @@ struct PinnedAllocator {
 };
 template <class T> using PinnedVec = std::vector<T, PinnedAllocator<T>>;
 
+// The device layout of a BVH (wide_bvh.h): built once on the host next to the reference-format node array, uploaded as is.
+struct WideBVH {
+    PinnedVec<WPair> pairs;              // records of three sibling pairs, depth-first
+    std::vector<WBigLeaf> big_leaves;    // leaves holding more than BPT_WREF_INLINE_COUNT_MAX items
+    WChild root{};                       // the tree root as a child record (it is box-tested like any node, intersection.cpp:269-277)
+    uint32_t depth = 0;                  // deepest leaf below the root = most far children one ray can have pending
+    int  mode = 0;
+    bool valid = false;
+};
+
 struct HostBVH {
     PinnedVec<bpt_bvh_node> nodes;       // bit-identical to BVH::nodes[0..node_count) (bvh.h:39-45)
     PinnedVec<uint32_t>     indices;     // BVH::indices
     float max_abs_extent = 0.0f;         // max over nodes/axes of |bv_p| + |bv_r| (NaN/inf propagate): FMNMX slab-test precondition
+    WideBVH wide;                        // the same tree as the device reads it
 };
 
 struct HostMesh {
@@ -94,6 +106,10 @@ void build_mesh_bvh(HostMesh* mesh);
 void build_bvh(std::vector<SortEntry>& entries, HostBVH* out, int method);      // BPT_BVH_* (bvh.h:7-11)
 void build_mesh_bvh(HostMesh* mesh, int method);
 void build_scene_bvh(bpt_scene* scene);
+
+// wide_bvh.cpp: re-layout into two-level pair records (validates the node array; BPT_ERR_ARG when it is malformed)
+int build_wide_bvh(const bpt_bvh_node* nodes, uint32_t node_count, uint32_t item_count, WideBVH* out, int mode);
+int build_wide_bvh(HostBVH* bvh, uint32_t item_count);
 
 // host_scene.cpp
 void recompute_camera(bpt_camera* camera);

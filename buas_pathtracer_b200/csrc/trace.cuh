@@ -4,14 +4,18 @@
 // Re-designed for SIMT rather than transcribed:
 //   * one flattened state machine walks TLAS and BLAS with a single per-thread stack (the reference nests
 //     intersect_mesh's loop inside the TLAS leaf loop, which would serialise a warp);
-//   * an inner node fetches BOTH children as one 64-byte sibling record (4 x LDG.128) and slab-tests them
-//     together; the near child is entered directly, the far child is pushed with its entry distance.
+//   * nodes are read as 64-byte sibling pairs grouped into two-level records (wide_bvh.h): entering a record root the
+//     lane fetches the node's child pair AND the near child's pair with eight 128-bit loads issued together, slab-tests
+//     all four boxes and replays the binary visit order in registers -- one dependent memory round trip per two levels;
+//   * the traversal stack holds 8-byte entries {child ref, entry distance}; its newest 8 entries live in shared memory
+//     (a window that follows the stack top), older ones spill to local memory only when the window overflows.
 // Equivalence argument (tie semantics): the reference pushes far then near and
 // re-tests each box when popped, against the t of that moment.  (tn < tf && tf > 0) does not depend on t, so
 // it is evaluated once at the parent; `tn < t` is evaluated for the near child immediately (nothing happens
-// between the reference's push and pop of it) and for the far child when it is popped, with the stored tn.
-// Leaves are therefore visited in the reference's order with the reference's culling, so equal-t ties
-// (`t <= out_t` accepts, intersection.cpp:174) resolve to the same triangle.
+// between the reference's push and pop of it) and for the far child when it is popped, with the stored tn.  The second
+// level of a record step is exactly the step the reference performs next (the near child was just accepted and t has
+// not changed), executed from registers.  Leaves are therefore visited in the reference's order with the reference's
+// culling, so equal-t ties (`t <= out_t` accepts, intersection.cpp:174) resolve to the same triangle.
 #pragma once
 #include "device_math.cuh"
 #include "device_scene.cuh"
@@ -146,157 +150,159 @@ struct TraceCounters {   // per-thread, flushed by the caller
     uint32_t tlas_pops, instances, mesh_calls, blas_pops, blas_inner, blas_leaves, tris;
 };
 
-#ifndef BPT_STACK_TOP_IN_REGS
-#define BPT_STACK_TOP_IN_REGS 0
+#define BPT_STACK_DEPTH 64        // the reference's node_stack[64] (intersection.cpp:261, :445); far children only here
+#ifndef BPT_SSTACK
+#define BPT_SSTACK 8              // the first BPT_SSTACK stack entries of a thread live in shared memory, deeper ones in local memory
 #endif
-#define BPT_STACK_DEPTH 64     // the reference's node_stack[64] (intersection.cpp:261, :445), far children only here
-
-// Per-lane traversal state.  begin() does what precedes the reference's node loop (planes + TLAS root pop); the
-// node / triangle / instance steps are driven by persistent_trace below, which is the ONLY traversal loop in the
-// library (render passes and the bpt_trace diagnostic both run it).
-struct TraversalStack {
-    float4 e[BPT_STACK_DEPTH];     // {left_first, count|axis<<16, entry distance, -}: one STL.128 / LDL.128 per push / pop
-};
+#ifndef BPT_TWO_LEVEL
+#define BPT_TWO_LEVEL 0           // 1: record roots fetch the near child's pair together with their own and take two levels per step
+#endif                            //    (measured on B200, C2: traversal 51.2 ms against 44.9 ms with one level per step -- see DESIGN.md)
+#define BPT_TRACE_THREADS 128     // block size of every kernel that runs persistent_trace
+#ifndef BPT_TRIP_LIMIT
+#define BPT_TRIP_LIMIT (1u << 28) // scheduling-loop trips per warp; ~400x the largest legitimate count (a 64 Mi-slot batch)
+#endif
 
 // MODE: 0 = closest hit (intersect_scene), 1 = occlusion (intersect_shadow_ray), 2 = per ray (Src::load says which)
 enum { TRACE_MODE_CLOSEST = 0, TRACE_MODE_OCCLUSION = 1, TRACE_MODE_MIXED = 2 };
 
-template <int MODE, bool STATS>
-struct Traversal {
-    enum { S_NODE, S_ITEMS, S_POP, S_DONE };
-
-    RayT ray;                            // ray in the current space (world in the TLAS, object inside a BLAS)
-    V3 wo, wd, winv;                     // world-space ray, restored when intersect_mesh "returns"
-    uint32_t wneg;
-    float t;
-    uint32_t hit_prim, hit_tri;
-    float hit_v, hit_w;
-    uint32_t cur_lf, cur_ca;
-    uint32_t leaf_i, leaf_end;           // TLAS leaf items still to test
-    uint32_t cur_prim, cur_tri_base, ignored;
-    bool occ;                            // TRACE_MODE_MIXED: this ray is a shadow ray
-    const DNodeHalf* nodes;
-    int sp, blas_sp, state, level;       // level: 0 = TLAS, 1 = inside a mesh BLAS
-    uint32_t c_pops, c_inner, c_leaves;  // per intersect_mesh call; dropped on an occlusion early-out like g_stats
-    // the stack itself lives outside the struct (TraversalStack) so these scalars stay in registers
-
-    BPT_D bool done() const { return state == S_DONE; }
-
-    BPT_D void begin(const DScene& sc, V3 o, V3 d, float max_t, uint32_t ignored_prim, TraceCounters& ctr) {
-        wo = o; wd = d;
-        make_ray(ray, o, d);
-        winv = ray.inv; wneg = ray.neg;
-        t = max_t;
-        hit_prim = BPT_HIT_MISS; hit_tri = 0xFFFFFFFFu; hit_v = 0.0f; hit_w = 0.0f;
-        ignored = ignored_prim;
-        sp = 0; blas_sp = 0; level = 0; leaf_i = 0; leaf_end = 0; cur_prim = 0; cur_tri_base = 0;
-        c_pops = c_inner = c_leaves = 0;
-        nodes = sc.tlas_nodes;
-        // planes first, linearly (intersection.cpp:424-433); in occlusion mode a plane hit does not return early
-        for (uint32_t i = 0; i < sc.plane_count; ++i) {
-            const DPlane& pl = sc.planes[i];
-            if (plane_test(ray, v3(__ldg(&pl.n[0]), __ldg(&pl.n[1]), __ldg(&pl.n[2])), __ldg(&pl.d), t)) hit_prim = BPT_HIT_PLANE | i;
-        }
-        // TLAS root (popped and box-tested like any node, intersection.cpp:450-454)
-        float4 q0 = __ldg(&nodes[0].q0), q1 = __ldg(&nodes[0].q1);
-        float tn;
-        bool hit = slab_test(ray, q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, tn) && (tn < t);
-        if (!(ray.neg & BPT_RAY_TAME)) hit = hit && parallel_axes_may_contain(ray, q0.x, q0.y, q0.z, q0.w, q1.x, q1.y);
-        if (STATS) ctr.tlas_pops += 1;
-        cur_lf = __float_as_uint(q1.z); cur_ca = __float_as_uint(q1.w);
-        state = hit ? S_NODE : S_DONE;
-    }
-
-    BPT_D void result(HitRecord& out) const {
-        out.t = t; out.prim = hit_prim; out.tri = hit_tri; out.v = hit_v; out.w = hit_w;
-    }
+// Per-CTA shared memory of a traversal kernel; [..][thread] so that a warp's accesses are conflict-free whatever each
+// lane's stack height is.  Besides the short stack it holds the per-ray state that the inner loop does not touch: that
+// state would otherwise occupy registers the two-level node step needs for its loads.
+struct TraceShared {
+    uint2    stack[BPT_SSTACK][BPT_TRACE_THREADS];   // {child ref, entry distance} of stack positions 0 .. BPT_SSTACK-1
+    float    wray[6][BPT_TRACE_THREADS];             // the world-space ray (o, d) while the lane is inside a mesh BLAS
+    uint32_t items_first[BPT_TRACE_THREADS];         // rest of the TLAS leaf's item loop, resumed when intersect_mesh "returns"
+    uint32_t items_count[BPT_TRACE_THREADS];
+    uint32_t ignored[BPT_TRACE_THREADS];             // ignored_primitive_index of the lane's ray
+    uint32_t index[BPT_TRACE_THREADS];               // which ray of the source the lane is tracing
+    uint32_t hit_prim[BPT_TRACE_THREADS];            // the hit record so far (t itself stays in a register: every pop reads it)
+    uint32_t hit_tri[BPT_TRACE_THREADS];
+    float    hit_v[BPT_TRACE_THREADS], hit_w[BPT_TRACE_THREADS];
+    uint32_t cur_prim[BPT_TRACE_THREADS];            // the instance whose BLAS the lane is in, and that mesh's first triangle
+    uint32_t tri_base[BPT_TRACE_THREADS];
 };
 
 // Persistent-warp traversal with lane refill and warp-level phase scheduling.
 //
 // Measured problem with a per-thread state machine (ncu, profiles/r1_trace_v1.txt): for incoherent rays only 3-8 of 32
 // lanes were active per issued instruction, because at any moment the lanes of a warp sit in different phases
-// (slab-testing a sibling pair / testing a triangle / transforming the ray into an instance / idle) and the warp
+// (slab-testing node pairs / testing triangles / transforming the ray into an instance / idle) and the warp
 // serialises over all of them every iteration, and because finished lanes idle until the slowest ray of the warp ends.
-// Here each lane still owns one ray (its Traversal stays in registers) but per iteration the WARP executes only
-// the phase that most of its lanes are waiting for -- ballot + popc pick it -- and "idle" is one of the phases: when
-// idle lanes are the largest group (and rays remain) they fetch new rays with one warp-aggregated atomicAdd and run
+// Here each lane still owns one ray (its traversal state stays in registers / shared memory) but per iteration the WARP
+// executes only the phase that most of its lanes are waiting for -- one REDUX picks it -- and "idle" is one of the phases:
+// when idle lanes are the largest group (and rays remain) they fetch new rays with one warp-aggregated atomicAdd and run
 // begin().  Every ray still performs exactly the reference's sequence of tests; only the interleaving between
 // independent rays changes.   Src supplies load(i, o, d, max_t, ignored, occ) / store(i, hit).
 // LOCAL = true: there is no shared ray queue; every lane produces its own rays -- Src supplies pending() and
 // bool next(o, d, max_t, ignored, occ) instead of load(); next() may do arbitrary per-lane work (k_tail shades the
 // lane's path there) -- and the call returns when no lane has anything pending.
+// This is the ONLY traversal loop in the library (render passes, the recursive integrators and the bpt_trace diagnostic
+// all run it).  Must be called by all BPT_TRACE_THREADS threads of the block, whole warps converged.
 template <int MODE, bool STATS, bool LOCAL, class Src>
 BPT_D void persistent_trace(const DScene& sc, Src& src, uint32_t n, uint32_t* cursor, uint32_t refill, TraceCounters& ctr) {
-    typedef Traversal<MODE, STATS> TV;
-    enum { P_IDLE = 0, P_INNER = 1, P_TRI = 2, P_ITEMS = 3 };
+    // P_RET: the lane's stack is down to its floor -- intersect_mesh returns (back to the TLAS leaf's item loop) or the
+    // ray is finished.  It votes with, and is handled inside, the P_ITEMS step so that the node / triangle steps carry
+    // nothing but their own work (their divergent tails were 25 % of the instructions at 8 of 32 lanes, ncu r2_trace_v7).
+    enum { P_IDLE = 0, P_INNER = 1, P_TRI = 2, P_ITEMS = 3, P_RET = 4 };
+    __shared__ TraceShared sh;
     const uint32_t FULL = 0xFFFFFFFFu;
-    const uint32_t lane = threadIdx.x & 31u;
-    TV tv;
-    TraversalStack stk;
-    tv.state = TV::S_DONE;
-    int phase = P_IDLE;
-    uint32_t tri_k = 0;
-    bool exhausted = false;
-    uint32_t my_index = 0;
-    const bool tame = sc.tame_bounds != 0;
-#if BPT_STACK_TOP_IN_REGS
-    float4 top = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-    bool top_valid = false;          // entry tv.sp-1 is in `top`, entries below it are in stk
-#endif
-    tv.occ = false;
-    auto occlusion = [&]() { return MODE == TRACE_MODE_MIXED ? tv.occ : (MODE == TRACE_MODE_OCCLUSION); };
+    const uint32_t tid = threadIdx.x, lane = tid & 31u;
 
-    // after `tv.cur_*` changed: which phase does the lane wait for now
-    auto classify = [&]() {
-        uint32_t count = tv.cur_ca & 0xFFFFu;
-        if (count == 0) phase = P_INNER;
-        else if (tv.level == 1) { phase = P_TRI; tri_k = 0; if (STATS) { tv.c_leaves += 1; ctr.tris += count; } }
-        else { tv.leaf_i = tv.cur_lf; tv.leaf_end = tv.cur_lf + count; phase = P_ITEMS; }
+    RayT ray;                                   // the ray in the current space (world in the TLAS, object inside a BLAS)
+    ray.o = v3(0.0f); ray.d = v3(0.0f); ray.inv = v3(0.0f); ray.neg = 0u;
+    float t = 0.0f;
+    uint32_t cur_a = 0u, cur_b = 0u;            // P_INNER: cur_a = ref of the inner node being entered;
+                                                // P_TRI / P_ITEMS: cur_a = next triangle / TLAS item of the leaf, cur_b = how many are left
+    uint32_t pair_base = 0u;
+    int sp = 0, blas_sp = -1;                   // stack height; height at which the current BLAS was entered (-1: in the TLAS)
+    bool occ = false;
+    uint32_t c_pops = 0u, c_inner = 0u, c_leaves = 0u;   // per intersect_mesh call; dropped on an occlusion early-out like g_stats
+    uint2 lstack[BPT_STACK_DEPTH - BPT_SSTACK]; // stack positions BPT_SSTACK .. 63 (local memory)
+    int phase = P_IDLE;
+    bool exhausted = false;
+    const bool tame = sc.tame_bounds != 0;
+    auto occlusion = [&]() { return MODE == TRACE_MODE_MIXED ? occ : (MODE == TRACE_MODE_OCCLUSION); };
+
+    auto push = [&](uint32_t ref, float tn) {
+        uint2 e = make_uint2(ref, __float_as_uint(tn));
+        if (sp < BPT_SSTACK) sh.stack[sp][tid] = e;
+        else if (sp < BPT_STACK_DEPTH) lstack[sp - BPT_SSTACK] = e;
+        else { *sc.error_flag = BPT_DEVERR_STACK_OVERFLOW; return; }     // the reference overruns node_stack[64] here
+        ++sp;
+    };
+    // a node has been accepted (its box test passed against the current t): which phase does the lane wait for now
+    auto enter = [&](uint32_t ref) {
+        if (!(ref & BPT_WREF_LEAF)) { cur_a = ref; phase = P_INNER; return; }
+        uint32_t count = (ref >> 28) & 7u, first = ref & BPT_WREF_INDEX_MASK;
+        if (count == 0u) {                      // forced leaf with more than 7 items (bvh.cpp:254, :278): range is in the side table
+            uint32_t bb = blas_sp >= 0 ? __ldg(&sc.meshes[__ldg(&sc.primitives[sh.cur_prim[tid]].mesh)].big_base) : 0u;
+            uint2 bl = __ldg(&sc.big_leaves[bb + first]);
+            first = bl.x; count = bl.y;
+        }
+        cur_a = first; cur_b = count;
+        if (blas_sp >= 0) { phase = P_TRI; if (STATS) { c_leaves += 1u; ctr.tris += count; } }
+        else phase = P_ITEMS;
     };
     auto finish = [&]() {
-        HitRecord h; tv.result(h); src.store(my_index, h);
+        HitRecord h; h.t = t; h.prim = sh.hit_prim[tid]; h.tri = sh.hit_tri[tid]; h.v = sh.hit_v[tid]; h.w = sh.hit_w[tid];
+        src.store(sh.index[tid], h);
         phase = P_IDLE;
     };
-    // the reference's "pop until a node survives its box re-test" (intersection.cpp:269-277, :450-454)
-    auto pop = [&]() {
-        for (;;) {
-            if (tv.level == 1 && tv.sp == tv.blas_sp) {
-                if (STATS) { ctr.blas_pops += tv.c_pops; ctr.blas_inner += tv.c_inner; ctr.blas_leaves += tv.c_leaves; }
-                tv.level = 0; tv.nodes = sc.tlas_nodes;
-                tv.ray.o = tv.wo; tv.ray.d = tv.wd; tv.ray.inv = tv.winv; tv.ray.neg = tv.wneg;   // == make_ray(wo, wd) again
-                phase = P_ITEMS;            // intersect_mesh returned: continue the TLAS leaf's item loop
-                return;
-            }
-            if (tv.sp == 0) { finish(); return; }
-            --tv.sp;
-#if BPT_STACK_TOP_IN_REGS
-            // the newest entry lives in registers: a push that is popped before the next push never touches memory
-            float4 e;
-            if (top_valid) { e = top; top_valid = false; }
-            else e = stk.e[tv.sp];
-#else
-            float4 e = stk.e[tv.sp];
-#endif
-            if (e.z < tv.t) { tv.cur_lf = __float_as_uint(e.x); tv.cur_ca = __float_as_uint(e.y); classify(); return; }
+    // the reference's "pop until a node survives its box re-test" (intersection.cpp:269-277, :450-454); when the stack is
+    // down to the floor of the current traversal the lane goes to P_RET
+    auto pop_enter = [&]() {
+        const int floor = blas_sp > 0 ? blas_sp : 0;
+        while (sp > floor) {
+            --sp;
+            uint2 e;
+            if (sp < BPT_SSTACK) e = sh.stack[sp][tid]; else e = lstack[sp - BPT_SSTACK];
+            if (__uint_as_float(e.y) < t) { enter(e.x); return; }
         }
+        phase = P_RET;
+    };
+    // ray_intersect_bounding_volume minus its `tn < t` clause, for any ray
+    auto slab_any = [&](const RayT& r, const float4& q0, const float4& q1, float& tn) {
+        bool h = slab_test(r, q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, tn);
+        if (!(r.neg & BPT_RAY_TAME)) h = h && parallel_axes_may_contain(r, q0.x, q0.y, q0.z, q0.w, q1.x, q1.y);
+        return h;
+    };
+    // what precedes the reference's node loop: planes, then the TLAS root is popped and box-tested like any node
+    auto begin = [&](V3 o, V3 d, float max_t, uint32_t ignored_prim) {
+        make_ray(ray, o, d);
+        if (!tame) ray.neg &= ~BPT_RAY_TAME;    // node boxes beyond 1e15: every ray takes the exact compare+select slab test
+        t = max_t;
+        uint32_t hp = BPT_HIT_MISS;
+        sh.ignored[tid] = ignored_prim;
+        sp = 0; blas_sp = -1; pair_base = 0u;
+        // planes first, linearly (intersection.cpp:424-433); in occlusion mode a plane hit does not return early
+        for (uint32_t i = 0; i < sc.plane_count; ++i) {
+            const DPlane& pl = sc.planes[i];
+            if (plane_test(ray, v3(__ldg(&pl.n[0]), __ldg(&pl.n[1]), __ldg(&pl.n[2])), __ldg(&pl.d), t)) hp = BPT_HIT_PLANE | i;
+        }
+        sh.hit_prim[tid] = hp; sh.hit_tri[tid] = 0xFFFFFFFFu; sh.hit_v[tid] = 0.0f; sh.hit_w[tid] = 0.0f;
+        float tn;
+        bool hit = slab_any(ray, sc.tlas_root_q0, sc.tlas_root_q1, tn) && (tn < t);      // intersection.cpp:450-454
+        if (STATS) ctr.tlas_pops += 1u;
+        if (hit) enter(__float_as_uint(sc.tlas_root_q1.z)); else finish();
     };
 
-    // The scheduling loop.  Its trip count is bounded on purpose: with a plain `for (;;)` whose only exit is the vote
-    // below, nvcc 12.9 rotates the loop and peels its first iteration, and the resulting k_trace_merged hung on
-    // B200 (deterministically, BASELINE config 4 at >= 16 spp: launch of bounce 3 never returned; every
-    // instrumented build ran through, and so did the same PTX assembled with ptxas -O0; -O1 and above hang).  A second,
-    // never-taken exit at the loop head keeps the loop in its source shape; tests/test_gpu_golden_and_fullsize.py::test_no_hang_* pins the behaviour.
-#ifdef BPT_DBG_PLAIN_LOOP            /* reproduces the hang described above; for investigating it only */
+    // The scheduling loop.  Its trip count is bounded: with a plain `for (;;)` whose only exit is the vote below, nvcc
+    // 12.9 rotated the loop and peeled its first iteration, and that build of k_trace_merged hung on B200
+    // (deterministically, BASELINE config 4 at >= 16 spp; every instrumented build ran through, and so did the same PTX
+    // assembled with ptxas -O0; -O1 and above hung).  An exit at the loop head keeps the loop in its source shape --
+    // tests/test_gpu_golden_and_fullsize.py::test_no_hang_* pins that -- and the bound is a real one: a warp that
+    // exceeds it raises BPT_DEVERR_TRIP_LIMIT and leaves, so a scheduling bug ends as an error code, not a hung GPU.
+    uint32_t trips = 0;
+#ifdef BPT_DBG_PLAIN_LOOP            /* the shape that hung; for investigating it only */
     for (;;) {
 #else
-    for (unsigned long long trips = 0; trips != ~0ull; ++trips) {
+    for (; trips != BPT_TRIP_LIMIT; ++trips) {
 #endif
         // phase populations of the warp, one byte each, from a single warp-wide add (REDUX.SUM)
-        // (an idle lane that cannot get another ray votes for nothing)
+        // (an idle lane that cannot get another ray votes for nothing; P_RET votes with P_ITEMS)
         bool can_fetch;
         if constexpr (LOCAL) can_fetch = src.pending(); else can_fetch = !exhausted;
-        uint32_t counts = __reduce_add_sync(FULL, (phase == P_IDLE && !can_fetch) ? 0u : (1u << (8*phase)));
+        uint32_t counts = __reduce_add_sync(FULL, (phase == P_IDLE && !can_fetch) ? 0u : (1u << (8*min(phase, (int)P_ITEMS))));
         if (counts == 0u) break;
         uint32_t n_inner = (counts >> 8) & 0xFFu, n_tri = (counts >> 16) & 0xFFu, n_items = counts >> 24;
         uint32_t n_idle = counts & 0xFFu;
@@ -312,12 +318,8 @@ BPT_D void persistent_trace(const DScene& sc, Src& src, uint32_t n, uint32_t* cu
                 V3 o, d; float max_t; uint32_t ign;
                 bool is_occ = false;
                 if (src.next(o, d, max_t, ign, is_occ)) {       // false: the lane's path ended without another ray
-                    tv.occ = is_occ;
-                    tv.begin(sc, o, d, max_t, ign, ctr);
-#if BPT_STACK_TOP_IN_REGS
-                    top_valid = false;
-#endif
-                    if (tv.done()) finish(); else classify();
+                    occ = is_occ;
+                    begin(o, d, max_t, ign);
                 }
             }
           } else {
@@ -332,13 +334,9 @@ BPT_D void persistent_trace(const DScene& sc, Src& src, uint32_t n, uint32_t* cu
                     V3 o, d; float max_t; uint32_t ign;
                     bool is_occ = false;
                     src.load(idx, o, d, max_t, ign, is_occ);
-                    tv.occ = is_occ;
-                    my_index = idx;
-                    tv.begin(sc, o, d, max_t, ign, ctr);
-#if BPT_STACK_TOP_IN_REGS
-                    top_valid = false;
-#endif
-                    if (tv.done()) finish(); else classify();
+                    occ = is_occ;
+                    sh.index[tid] = idx;
+                    begin(o, d, max_t, ign);
                 }
             }
             if (base + nid >= n) exhausted = true;
@@ -348,93 +346,159 @@ BPT_D void persistent_trace(const DScene& sc, Src& src, uint32_t n, uint32_t* cu
           uint32_t keep = max(best - (best >> 2), 1u);
           do {
             if (phase == P_INNER) {
-                // the parent's split axis and the ray's sign say which child is near (intersection.cpp:303-318):
-                // fetch them in that order so nothing has to be swapped afterwards
-                uint32_t right_first = (tv.ray.neg >> (tv.cur_ca >> 16)) & 1u;
-                const DNodeHalf* pn = tv.nodes + (tv.cur_lf + right_first);
-                const DNodeHalf* pf = tv.nodes + (tv.cur_lf + (right_first ^ 1u));
+                // the node's split axis and the ray's sign say which child is near (intersection.cpp:303-318): known
+                // before anything is loaded, so the children are fetched in near/far order
+                const uint32_t ref = cur_a;
+                const uint32_t k = (ray.neg >> (ref >> 29)) & 1u;                   // bit 31 is clear: ref >> 29 is the axis
+                const DPair* pp = sc.pairs + (pair_base + (ref & BPT_WREF_INDEX_MASK));
+                const DChild* pn = &pp->c[k];
+                const DChild* pf = &pp->c[k ^ 1u];
                 float4 n0 = __ldg(&pn->q0), n1 = __ldg(&pn->q1);
                 float4 f0 = __ldg(&pf->q0), f1 = __ldg(&pf->q1);
+#if BPT_TWO_LEVEL
+                // at a record root the near child's own pair sits right behind the node's pair: fetch it along
+                const bool two = (ref & BPT_WREF_RECORD_ROOT) != 0u && (ray.neg & BPT_RAY_TAME);
+                float4 a0, a1, b0, b1;
+                if (two) {
+                    const DPair* pg = pp + 1 + k;
+                    a0 = __ldg(&pg->c[0].q0); a1 = __ldg(&pg->c[0].q1);
+                    b0 = __ldg(&pg->c[1].q0); b1 = __ldg(&pg->c[1].q1);
+                }
+#endif
                 float near_tn, far_tn;
                 bool near_hit, far_hit;
-                if (tame && (tv.ray.neg & BPT_RAY_TAME)) {
-                    near_hit = slab_test_tame(tv.ray, n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, near_tn);
-                    far_hit  = slab_test_tame(tv.ray, f0.x, f0.y, f0.z, f0.w, f1.x, f1.y, far_tn);
+                if (ray.neg & BPT_RAY_TAME) {
+                    near_hit = slab_test_tame(ray, n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, near_tn);
+                    far_hit  = slab_test_tame(ray, f0.x, f0.y, f0.z, f0.w, f1.x, f1.y, far_tn);
                 } else {
-                    near_hit = slab_test(tv.ray, n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, near_tn);
-                    far_hit  = slab_test(tv.ray, f0.x, f0.y, f0.z, f0.w, f1.x, f1.y, far_tn);
-                    near_hit = near_hit && parallel_axes_may_contain(tv.ray, n0.x, n0.y, n0.z, n0.w, n1.x, n1.y);
-                    far_hit  = far_hit  && parallel_axes_may_contain(tv.ray, f0.x, f0.y, f0.z, f0.w, f1.x, f1.y);
+                    // rays with a zero / denormal / huge direction component: the exact compare+select slab test
+                    near_hit = slab_any(ray, n0, n1, near_tn);
+                    far_hit  = slab_any(ray, f0, f1, far_tn);
                 }
-                if (STATS) { if (tv.level) { tv.c_pops += 2; tv.c_inner += 1; } else ctr.tlas_pops += 2; }
-                uint32_t near_lf = __float_as_uint(n1.z), near_ca = __float_as_uint(n1.w);
-                if (far_hit && tv.sp < BPT_STACK_DEPTH) {
-#if BPT_STACK_TOP_IN_REGS
-                    if (top_valid) stk.e[tv.sp - 1] = top;              // the previous newest entry moves to memory
-                    top = make_float4(f1.z, f1.w, far_tn, 0.0f); top_valid = true; ++tv.sp;
-#else
-                    stk.e[tv.sp] = make_float4(f1.z, f1.w, far_tn, 0.0f); ++tv.sp;
+                if (STATS) { if (blas_sp >= 0) { c_pops += 2u; c_inner += 1u; } else ctr.tlas_pops += 2u; }
+                // The reference pushes far then near and pops: near is re-tested against the unchanged t; when it fails, far
+                // is popped next and re-tested against the same t.  So: near accepted -> far (if its box is hit) waits on
+                // the stack; near rejected -> far is entered directly if it would pass, and is never pushed otherwise.
+                const uint32_t nref = __float_as_uint(n1.z), fref = __float_as_uint(f1.z);
+                const bool go_near = near_hit && near_tn < t;
+                const bool go_far = !go_near && far_hit && far_tn < t;
+                if (go_near && far_hit) push(fref, far_tn);
+#if BPT_TWO_LEVEL
+                if (go_near && two && !(nref & BPT_WREF_LEAF)) {
+                    // the step the reference performs next, from registers: the near child was accepted, t is unchanged
+                    float a_tn, b_tn;
+                    bool a_hit = slab_test_tame(ray, a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a_tn);
+                    bool b_hit = slab_test_tame(ray, b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b_tn);
+                    if (STATS) { if (blas_sp >= 0) { c_pops += 2u; c_inner += 1u; } else ctr.tlas_pops += 2u; }
+                    const bool right_first = ((ray.neg >> (nref >> 29)) & 1u) != 0u;
+                    bool     h_near = right_first ? b_hit : a_hit,   h_far = right_first ? a_hit : b_hit;
+                    float    t_near = right_first ? b_tn : a_tn,     t_far = right_first ? a_tn : b_tn;
+                    uint32_t r_near = __float_as_uint(right_first ? b1.z : a1.z), r_far = __float_as_uint(right_first ? a1.z : b1.z);
+                    const bool go2_near = h_near && t_near < t;
+                    const bool go2_far = !go2_near && h_far && t_far < t;
+                    if (go2_near && h_far) push(r_far, t_far);
+                    if (go2_near || go2_far) enter(go2_near ? r_near : r_far); else pop_enter();
+                } else
 #endif
-                }
-                if (near_hit && near_tn < tv.t) { tv.cur_lf = near_lf; tv.cur_ca = near_ca; classify(); }
-                else pop();
+                if (go_near || go_far) enter(go_near ? nref : fref);
+                else pop_enter();
             }
           } while (__popc(__ballot_sync(FULL, phase == P_INNER)) >= keep);
         } else if (run == P_TRI) {
           uint32_t keep = max(best - (best >> 2), 1u);
           do {
             if (phase == P_TRI) {
-                uint32_t slot = tv.cur_tri_base + tv.cur_lf + tri_k;
-                const DTriangle* tri = sc.triangles + slot;
-                float4 a = __ldg(&tri->a_idx), e1 = __ldg(&tri->e1), e2 = __ldg(&tri->e2);
-                bool stop = false;
-                if (triangle_test(tv.ray, v3(a), v3(e1), v3(e2), tv.t, tv.hit_v, tv.hit_w)) {
-                    tv.hit_tri = slot;
-                    tv.hit_prim = tv.cur_prim;
-                    if (occlusion()) { finish(); stop = true; }
+                // up to two triangles of the leaf per step, fetched together, tested in the reference's order
+                if (cur_b == 0u) {
+                    pop_enter();
+                } else {
+                    const uint32_t slot = sh.tri_base[tid] + cur_a;
+                    const DTriangle* tri = sc.triangles + slot;
+                    const bool second = cur_b > 1u;
+                    float4 a = __ldg(&tri->a_idx), e1 = __ldg(&tri->e1), e2 = __ldg(&tri->e2);
+                    float4 a2 = a, e12 = e1, e22 = e2;
+                    if (second) { a2 = __ldg(&tri[1].a_idx); e12 = __ldg(&tri[1].e1); e22 = __ldg(&tri[1].e2); }
+                    bool stop = false;
+                    float v, w;
+                    if (triangle_test(ray, v3(a), v3(e1), v3(e2), t, v, w)) {
+                        sh.hit_tri[tid] = slot; sh.hit_prim[tid] = sh.cur_prim[tid]; sh.hit_v[tid] = v; sh.hit_w[tid] = w;
+                        if (occlusion()) { finish(); stop = true; }
+                    }
+                    if (!stop && second) {
+                        if (triangle_test(ray, v3(a2), v3(e12), v3(e22), t, v, w)) {
+                            sh.hit_tri[tid] = slot + 1u; sh.hit_prim[tid] = sh.cur_prim[tid]; sh.hit_v[tid] = v; sh.hit_w[tid] = w;
+                            if (occlusion()) { finish(); stop = true; }
+                        }
+                    }
+                    if (!stop) {
+                        uint32_t adv = second ? 2u : 1u;
+                        cur_a += adv; cur_b -= adv;
+                        if (cur_b == 0u) pop_enter();
+                    }
                 }
-                if (!stop && ++tri_k >= (tv.cur_ca & 0xFFFFu)) pop();
             }
           } while (__popc(__ballot_sync(FULL, phase == P_TRI)) >= keep);
         } else {
-            if (phase == P_ITEMS) {
-                if (tv.leaf_i >= tv.leaf_end) {
-                    pop();
+            if (phase == P_RET) {
+                if (blas_sp >= 0) {
+                    // intersect_mesh returns: back to the world-space ray and the TLAS leaf's item loop
+                    if (STATS) { ctr.blas_pops += c_pops; ctr.blas_inner += c_inner; ctr.blas_leaves += c_leaves; }
+                    blas_sp = -1; pair_base = 0u;
+                    make_ray(ray, v3(sh.wray[0][tid], sh.wray[1][tid], sh.wray[2][tid]),
+                                  v3(sh.wray[3][tid], sh.wray[4][tid], sh.wray[5][tid]));    // the world ray again (same values: same operations)
+                    if (!tame) ray.neg &= ~BPT_RAY_TAME;
+                    cur_a = sh.items_first[tid]; cur_b = sh.items_count[tid];
+                    phase = P_ITEMS;
                 } else {
-                    uint32_t prim_index = __ldg(&sc.tlas_indices[tv.leaf_i++]);
-                    if (prim_index != tv.ignored) {
+                    finish();                   // the TLAS stack is empty: intersect_scene_internal returns
+                }
+            }
+            if (phase == P_ITEMS) {
+                if (cur_b == 0u) {
+                    pop_enter();
+                } else {
+                    uint32_t prim_index = __ldg(&sc.tlas_indices[cur_a]);
+                    ++cur_a; --cur_b;
+                    if (prim_index != sh.ignored[tid]) {
                         const DPrimitive* prim = sc.primitives + prim_index;
                         float4 m[3] = {__ldg(&prim->inv[0]), __ldg(&prim->inv[1]), __ldg(&prim->inv[2])};
                         RayT oray;
-                        oray.o = xform(m, tv.wo, 1.0f); oray.d = xform(m, tv.wd, 0.0f);     // transform_ray :403-409
-                        if (STATS) ctr.instances += 1;
+                        oray.o = xform(m, ray.o, 1.0f); oray.d = xform(m, ray.d, 0.0f);     // transform_ray :403-409
+                        oray.inv = v3(0.0f); oray.neg = 0u;
+                        if (STATS) ctr.instances += 1u;
                         uint32_t type = __ldg(&prim->type);
-                        if (type != BPT_PRIM_SPHERE) make_ray(oray, oray.o, oray.d);        // the sphere test never reads inv_d
+                        if (type != BPT_PRIM_SPHERE) {                                      // the sphere test never reads inv_d
+                            make_ray(oray, oray.o, oray.d);
+                            if (!tame) oray.neg &= ~BPT_RAY_TAME;
+                        }
                         if (type == BPT_PRIM_SPHERE) {
-                            if (sphere_test(oray, __ldg(&prim->sphere_r), tv.t)) {
-                                tv.hit_prim = prim_index; tv.hit_tri = 0xFFFFFFFFu;
+                            if (sphere_test(oray, __ldg(&prim->sphere_r), t)) {
+                                sh.hit_prim[tid] = prim_index; sh.hit_tri[tid] = 0xFFFFFFFFu;
                                 if (occlusion()) finish();
                             }
                         } else if (type == BPT_PRIM_BOX) {
-                            if (box_test(oray, __ldg(&prim->box_r[0]), __ldg(&prim->box_r[1]), __ldg(&prim->box_r[2]), tv.t)) {
-                                tv.hit_prim = prim_index; tv.hit_tri = 0xFFFFFFFFu;
+                            if (box_test(oray, __ldg(&prim->box_r[0]), __ldg(&prim->box_r[1]), __ldg(&prim->box_r[2]), t)) {
+                                sh.hit_prim[tid] = prim_index; sh.hit_tri[tid] = 0xFFFFFFFFu;
                                 if (occlusion()) finish();
                             }
                         } else if (type == BPT_PRIM_MESH) {
                             const DMesh* mesh = sc.meshes + __ldg(&prim->mesh);
-                            const DNodeHalf* bn = sc.blas_nodes + __ldg(&mesh->node_base);
-                            if (STATS) { ctr.mesh_calls += 1; tv.c_pops = 1; tv.c_inner = 0; tv.c_leaves = 0; }
-                            float4 q0 = __ldg(&bn[0].q0), q1 = __ldg(&bn[0].q1);
+                            if (STATS) { ctr.mesh_calls += 1u; c_pops = 1u; c_inner = 0u; c_leaves = 0u; }
+                            float4 q0 = __ldg(&mesh->root_q0), q1 = __ldg(&mesh->root_q1);
                             float tn;
-                            bool root_hit = slab_test(oray, q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, tn) && (tn < tv.t);
-                            if (!(oray.neg & BPT_RAY_TAME)) root_hit = root_hit && parallel_axes_may_contain(oray, q0.x, q0.y, q0.z, q0.w, q1.x, q1.y);
+                            bool root_hit = slab_any(oray, q0, q1, tn) && (tn < t);          // intersect_mesh pops its root first (:269-277)
                             if (root_hit) {
-                                tv.level = 1; tv.ray = oray; tv.nodes = bn; tv.blas_sp = tv.sp;
-                                tv.cur_prim = prim_index; tv.cur_tri_base = __ldg(&mesh->tri_base);
-                                tv.cur_lf = __float_as_uint(q1.z); tv.cur_ca = __float_as_uint(q1.w);
-                                classify();
+                                // intersect_mesh is "called": park the world-level state, switch to the object-space ray
+                                sh.wray[0][tid] = ray.o.x; sh.wray[1][tid] = ray.o.y; sh.wray[2][tid] = ray.o.z;
+                                sh.wray[3][tid] = ray.d.x; sh.wray[4][tid] = ray.d.y; sh.wray[5][tid] = ray.d.z;
+                                sh.items_first[tid] = cur_a; sh.items_count[tid] = cur_b;
+                                ray = oray; blas_sp = sp;
+                                pair_base = __ldg(&mesh->pair_base);
+                                sh.tri_base[tid] = __ldg(&mesh->tri_base);
+                                sh.cur_prim[tid] = prim_index;
+                                enter(__float_as_uint(q1.z));
                             } else if (STATS) {
-                                ctr.blas_pops += 1;
+                                ctr.blas_pops += 1u;
                             }
                         }
                     }
@@ -442,6 +506,9 @@ BPT_D void persistent_trace(const DScene& sc, Src& src, uint32_t n, uint32_t* cu
             }
         }
     }
+#ifndef BPT_DBG_PLAIN_LOOP
+    if (trips == BPT_TRIP_LIMIT) *sc.error_flag = BPT_DEVERR_TRIP_LIMIT;
+#endif
 }
 
 } // namespace bpt

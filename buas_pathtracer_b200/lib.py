@@ -11,6 +11,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = None
 
 # every symbol include/bpt.h declares (checked by tests/test_abi.py against the header itself)
+MULTI_GPU_SYMBOLS = ["nccl_get_unique_id", "nccl_comm_init_rank", "nccl_comm_init_all", "nccl_comm_destroy", "reduce_film",
+                     "reduced_film_device_ptr", "download_reduced_film"]
 DEVICE_SYMBOLS = [
     "create", "destroy", "set_sampler_tables", "upload_scene", "update_settings", "film_resize", "film_clear",
     "film_use_external", "film_device_ptr", "download_film", "render_pass", "render_pass_bands", "sync", "trace", "set_sample_records",
@@ -104,6 +106,24 @@ def load_library():
     L.bpt_resolve_bgra8.argtypes = [vp, P(capi.PostSettings), vp, C.c_uint32, C.c_uint32, vp]
     L.bpt_write_bitmap.restype = C.c_int
     L.bpt_write_bitmap.argtypes = [C.c_char_p, vp, C.c_uint32, C.c_uint32]
+    if hasattr(L, "bpt_reduce_film"):
+        L.bpt_nccl_get_unique_id.restype = C.c_int
+        L.bpt_nccl_get_unique_id.argtypes = [vp]
+        L.bpt_nccl_comm_init_rank.restype = C.c_int
+        L.bpt_nccl_comm_init_rank.argtypes = [vp, vp, C.c_int, C.c_int, P(vp)]
+        L.bpt_nccl_comm_init_all.restype = C.c_int
+        L.bpt_nccl_comm_init_all.argtypes = [C.c_int, vp, P(vp)]
+        L.bpt_nccl_comm_destroy.restype = C.c_int
+        L.bpt_nccl_comm_destroy.argtypes = [vp]
+        L.bpt_reduce_film.restype = C.c_int
+        L.bpt_reduce_film.argtypes = [vp, vp, C.c_int]
+        L.bpt_reduced_film_device_ptr.restype = C.c_int
+        L.bpt_reduced_film_device_ptr.argtypes = [vp, P(vp)]
+        L.bpt_download_reduced_film.restype = C.c_int
+        L.bpt_download_reduced_film.argtypes = [vp, vp]
+    if hasattr(L, "bpt_get_wide_bvh"):        # absent from older builds selected with BPT_LIBRARY for A/B runs
+        L.bpt_get_wide_bvh.restype = C.c_int
+        L.bpt_get_wide_bvh.argtypes = [vp, C.c_int32, P(vp), P(C.c_uint32), vp, P(vp), P(C.c_uint32), P(C.c_uint32)]
     _LIB = L
     return L
 
@@ -126,6 +146,23 @@ class Scene(capi.HostScene):
 
     def __init__(self):
         super().__init__(load_library(), "bpt_")
+
+    def wide_bvh(self, mesh=-1):
+        """The device layout of a BVH (csrc/wide_bvh.h) as (children[2*pairs] structured array, root child, big leaves
+        [n,2], depth); mesh < 0 = the TLAS.  Copies."""
+        L = self.lib
+        pairs, big = C.c_void_p(), C.c_void_p()
+        npairs, nbig, depth = C.c_uint32(), C.c_uint32(), C.c_uint32()
+        root = np.zeros(1, capi.WIDE_CHILD_DTYPE)
+        _check(L.bpt_get_wide_bvh(self.handle, int(mesh), C.byref(pairs), C.byref(npairs), root.ctypes.data, C.byref(big),
+                                  C.byref(nbig), C.byref(depth)), "bpt_get_wide_bvh")
+        children = np.zeros(2 * npairs.value, capi.WIDE_CHILD_DTYPE)
+        if npairs.value:
+            C.memmove(children.ctypes.data, pairs.value, children.nbytes)
+        bl = np.zeros((nbig.value, 2), np.uint32)
+        if nbig.value:
+            C.memmove(bl.ctypes.data, big.value, bl.nbytes)
+        return children, root[0], bl, depth.value
 
     def create_mesh_with_bvh(self, positions, nodes, indices, normals=None):
         """bpt_create_mesh with a caller-supplied BVH (e.g. Renderer.build_mesh_bvh) instead of the host build"""
@@ -261,6 +298,34 @@ class Renderer:
         if out is None:
             out = np.empty((self.h, self.w, 4), np.float32)
         _check(self.lib.bpt_download_film(self.handle, out.ctypes.data), "bpt_download_film")
+        return out
+
+    # -- multi-GPU (include/bpt.h section 3): one Renderer per rank, one NCCL reduce per progressive pass --
+    @staticmethod
+    def nccl_unique_id():
+        """ncclGetUniqueId as 128 bytes (rank 0 creates it and hands it to the other ranks)"""
+        buf = np.zeros(128, np.uint8)
+        _check(load_library().bpt_nccl_get_unique_id(buf.ctypes.data), "bpt_nccl_get_unique_id")
+        return buf
+
+    def nccl_comm_init_rank(self, unique_id, nranks, rank):
+        uid = np.ascontiguousarray(unique_id, np.uint8)
+        assert uid.size == 128
+        comm = C.c_void_p()
+        _check(self.lib.bpt_nccl_comm_init_rank(self.handle, uid.ctypes.data, nranks, rank, C.byref(comm)), "bpt_nccl_comm_init_rank")
+        return comm
+
+    def nccl_comm_destroy(self, comm):
+        _check(self.lib.bpt_nccl_comm_destroy(comm), "bpt_nccl_comm_destroy")
+
+    def reduce_film(self, comm, root=0):
+        """root's reduced film := sum of all ranks' films (asynchronous on the context's stream; partial films untouched)"""
+        _check(self.lib.bpt_reduce_film(self.handle, comm, root), "bpt_reduce_film")
+
+    def download_reduced_film(self, out=None):
+        if out is None:
+            out = np.empty((self.h, self.w, 4), np.float32)
+        _check(self.lib.bpt_download_reduced_film(self.handle, out.ctypes.data), "bpt_download_reduced_film")
         return out
 
     def trace(self, rays, mode=capi.TRACE_CLOSEST, ignored_primitive=0):

@@ -10,6 +10,18 @@ import numpy as np
 
 DEG_TO_RAD = np.float32(np.float32(6.28318530717) / np.float32(360.0))   # my_math.h:17
 
+# Who generates the procedural inputs (displaced icosphere, procedural HDR environment).  None = the product library
+# (bpt_make_* of include/bpt.h).  The reference arm of bench.py sets this to oracle.ref_inputs -- the same source file
+# built standalone -- so that it never loads libbpt.so.
+INPUTS = None
+
+
+def _inputs():
+    if INPUTS is not None:
+        return INPUTS
+    from . import lib
+    return lib
+
 
 def translate(v):
     """transform_translate (my_math.h:1026-1032) as (forward, inverse) 4x4 float32."""
@@ -70,9 +82,8 @@ def c1_week3(scene, w, h):
 def c2_icosphere(scene, w, h, level=8, tris=None):
     """BASELINE config 2: one displaced icosphere (level 8 = 1,310,720 triangles, flat normals) under the TLAS,
     a checker ground plane, one spherical light, constant sky."""
-    from .lib import make_displaced_icosphere
     if tris is None:
-        tris = make_displaced_icosphere(level, 0.08)
+        tris = _inputs().make_displaced_icosphere(level, 0.08)
     _camera(scene, w, h, (0, 4.5, -11), 50.0, look_at=(0, 3.5, 0))
     cam = scene.get_camera()
     cam.focus_distance = 1.0
@@ -94,11 +105,10 @@ def c3_instances(scene, w, h, level=7, grid=8, tris=None, sky=None, sky_size=(20
     """BASELINE config 3: grid x grid instances of one level-7 icosphere (327,680 triangles each; 64 instances =
     20,971,520 triangles) with per-instance translate*rotate*scale, lit by a procedural HDR environment map plus
     one spherical light."""
-    from .lib import make_displaced_icosphere, make_procedural_skydome
     if tris is None:
-        tris = make_displaced_icosphere(level, 0.08)
+        tris = _inputs().make_displaced_icosphere(level, 0.08)
     if sky is None:
-        sky = make_procedural_skydome(*sky_size)
+        sky = _inputs().make_procedural_skydome(*sky_size)
     _camera(scene, w, h, (0, 11, -26), 40.0, look_at=(0, 1.0, 0))
     cam = scene.get_camera()
     cam.focus_distance = 1.0
@@ -182,6 +192,48 @@ def whitted_showcase(scene, w, h):
     scene.add_sphere(l1, 0.5, translate((6.0, 14.0, -6.0)))
     scene.add_sphere(l2, 0.4, translate((-8.0, 9.0, -4.0)))
     scene.create_scene_bvh()
+
+
+def smooth_normals(tris):
+    """per-vertex normals of an (approximately) origin-centred mesh: the normalised vertex positions, (n, 9) like `tris`"""
+    v = np.asarray(tris, np.float32).reshape(-1, 3)
+    n = v / np.maximum(np.linalg.norm(v, axis=1, keepdims=True), 1e-20)
+    return n.astype(np.float32).reshape(-1, 9)
+
+
+def kitchen_sink(scene, w, h, level=3, tris=None, importance_sample_lights=1):
+    """Parity scene for the branches of the default integrator that the BASELINE configs never reach: thin-lens depth of
+    field with the polygonal-bokeh transform (lens_radius > 0, f_factor > 0, raytracer.cpp:86-94, :448-460); a rough metal,
+    a rough dielectric and a glossy-coated diffuse (random_in_unit_sphere rejection loop, integrators.cpp:684-696); three
+    sphere lights of different size and power (pick_random_light's CDF walk or uniform pick, :135-192); a rotated and
+    scaled mesh WITH per-vertex normals (interpolation + the reference's transform_normal, intersection.cpp:560-591); a
+    rotated box."""
+    if tris is None:
+        tris = _inputs().make_displaced_icosphere(level, 0.08)
+    _camera(scene, w, h, (0.5, 4.5, -10.5), 48.0, look_at=(0, 2.2, 0), lens_radius=5.0, focus_distance=10.5)
+    _advanced(scene, f_factor=0.7, diaphragm_edges=6.0, phi_shutter_max=0.5, max_bounce_count=10,
+              importance_sample_lights=int(importance_sample_lights))
+    scene.set_sky((0.35, 0.45, 0.7), (0.7, 0.65, 0.55))
+    ground = scene.add_diffuse_material((0.8, 0.8, 0.8), 1.0, 0.0, True, (0.2, 0.2, 0.25))
+    coated = scene.add_diffuse_material((0.2, 0.5, 0.85), 1.5, 0.2)
+    metal = scene.add_material(albedo=(0.9, 0.7, 0.3), ior=1.4, metallic=0.85, roughness=0.25)
+    frosted = scene.add_translucent_material((0.15, 0.35, 0.2), 1.5, 0.08)
+    clay = scene.add_diffuse_material((0.85, 0.5, 0.35), 1.3, 0.05)
+    l1 = scene.add_emissive_material((900, 850, 700))
+    l2 = scene.add_emissive_material((150, 250, 500))
+    l3 = scene.add_emissive_material((2500, 1200, 400))
+    scene.add_plane(ground, (0, 1, 0), 0.0)
+    scene.add_sphere(metal, 2.2, translate((4.5, 2.2, 2.0)))
+    scene.add_sphere(frosted, 2.0, translate((0.0, 2.0, -3.0)))
+    scene.add_sphere(coated, 1.5, translate((-5.5, 1.5, -1.0)))
+    mesh = scene.create_mesh(tris, normals=smooth_normals(tris))
+    scene.add_mesh(clay, mesh, trs((-2.5, 2.3, 4.0), 0.7, 2.0))
+    scene.add_box(coated, (1.0, 1.2, 0.8), trs((2.0, 1.2, -6.0), -0.5, 1.0))
+    scene.add_sphere(l1, 0.5, translate((6.0, 13.0, -6.0)))
+    scene.add_sphere(l2, 0.8, translate((-8.0, 8.0, -4.0)))
+    scene.add_sphere(l3, 0.25, translate((0.0, 9.0, 8.0)))
+    scene.create_scene_bvh()
+    return tris
 
 
 CONFIGS = {

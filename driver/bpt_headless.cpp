@@ -3,13 +3,20 @@
 //
 //   bpt_headless --tables sampler_tables.bin [--scene week3|icosphere|obj] [--obj file.obj [--cw]] [--hdr sky.hdr]
 //                [--integrator "Whitted"|...] [--filter "Gaussian 3"|...] [--gpu-bvh] [--w W --h H] [--spp N] [--passes P]
-//                [--level L] [--device D] [--out file.bmp]
+//                [--level L] [--device D] [--gpus N] [--out file.bmp]
+//
+// --gpus N: the frame is split into interleaved 8-row blocks over N GPUs of this box (one host thread and one bpt_ctx per
+// GPU, scene replicated), every progressive pass ends with ONE NCCL reduce of the partial films to GPU 0
+// (bpt_reduce_film), and GPU 0 resolves the summed film -- the multi-GPU analogue of the reference's worker threads
+// sharing one AccumulationBuffer (raytracer.cpp:551-603, :692-757).
 //
 // It only speaks include/bpt.h (plain C), exactly like a binding inside the reference would.
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <atomic>
 #include <chrono>
+#include <thread>
 #include <vector>
 
 #include "../include/bpt.h"
@@ -132,11 +139,34 @@ static int build_obj_scene(bpt_scene* s, bpt_ctx* ctx, uint32_t w, uint32_t h, c
 
 #define CHECK(call) do { int rc_ = (call); if (rc_ != BPT_OK) { fprintf(stderr, "%s failed (%d): %s\n", #call, rc_, bpt_last_error()); return 1; } } while (0)
 
+static const int kBlockRows = 8;      // interleave granularity of the row partition (block b -> GPU b % N)
+
+// one GPU's share of a multi-GPU render: its own context, the replicated scene, its row blocks, one reduce per pass
+static int render_rank(int rank, int n_gpus, int device, void* comm, const bpt_scene* scene, const uint8_t* blob,
+                       uint32_t w, uint32_t h, uint32_t spp, uint32_t passes, bpt_ctx** out_ctx, bpt_stats* out_stats) {
+    bpt_ctx* ctx = nullptr;
+    CHECK(bpt_create(device, &ctx));
+    *out_ctx = ctx;
+    CHECK(bpt_set_sampler_tables(ctx, blob, blob + 16384, blob + 81920, blob + 212992));
+    CHECK(bpt_upload_scene(ctx, scene));
+    CHECK(bpt_film_resize(ctx, w, h));
+    std::vector<int32_t> bands;
+    for (uint32_t b = 0, y0 = 0; y0 < h; ++b, y0 += kBlockRows)
+        if ((int)(b % (uint32_t)n_gpus) == rank) { bands.push_back((int32_t)y0); bands.push_back((int32_t)(y0 + kBlockRows < h ? y0 + kBlockRows : h)); }
+    for (uint32_t p = 0; p < passes; ++p) {
+        if (!bands.empty()) CHECK(bpt_render_pass_bands(ctx, 0, (int32_t)w, (uint32_t)bands.size()/2, bands.data(), p*spp, spp, BPT_SEED_PER_PIXEL, p));
+        CHECK(bpt_reduce_film(ctx, comm, 0));          // the partial films keep accumulating; the root's sum is refreshed
+    }
+    CHECK(bpt_sync(ctx));
+    CHECK(bpt_get_stats(ctx, out_stats, 0));
+    return 0;
+}
+
 int main(int argc, char** argv) {
     const char* scene_name = "week3"; const char* out = "render.bmp"; const char* tables = nullptr;
     const char* obj_path = nullptr; const char* hdr_path = nullptr; const char* integrator = nullptr; const char* filter = nullptr;
     int winding = BPT_WINDING_COUNTER_CLOCKWISE; bool gpu_bvh = false;
-    uint32_t w = 640, h = 360, spp = 16, passes = 1, level = 6; int device = 0;
+    uint32_t w = 640, h = 360, spp = 16, passes = 1, level = 6; int device = 0; int gpus = 1;
     for (int i = 1; i < argc; ++i) {
         auto next = [&]() -> const char* { return i + 1 < argc ? argv[++i] : ""; };
         if (!strcmp(argv[i], "--scene")) scene_name = next();
@@ -146,6 +176,7 @@ int main(int argc, char** argv) {
         else if (!strcmp(argv[i], "--passes")) passes = (uint32_t)atoi(next());
         else if (!strcmp(argv[i], "--level")) level = (uint32_t)atoi(next());
         else if (!strcmp(argv[i], "--device")) device = atoi(next());
+        else if (!strcmp(argv[i], "--gpus")) gpus = atoi(next());
         else if (!strcmp(argv[i], "--out")) out = next();
         else if (!strcmp(argv[i], "--tables")) tables = next();
         else if (!strcmp(argv[i], "--obj")) { obj_path = next(); scene_name = "obj"; }
@@ -157,6 +188,7 @@ int main(int argc, char** argv) {
         else { fprintf(stderr, "unknown argument %s\n", argv[i]); return 2; }
     }
     if (!tables) { fprintf(stderr, "--tables <sampler_tables.bin> is required (the sampler lookup tables, see INTEGRATION.md)\n"); return 2; }
+    if (gpus < 1 || gpus > 64) { fprintf(stderr, "--gpus must be 1..64\n"); return 2; }
     std::vector<uint8_t> blob(16384 + 65536 + 131072 + 131072);
     FILE* tf = fopen(tables, "rb");
     if (!tf || fread(blob.data(), 1, blob.size(), tf) != blob.size()) { fprintf(stderr, "cannot read %s\n", tables); return 2; }
@@ -179,24 +211,50 @@ int main(int argc, char** argv) {
     CHECK(bpt_create_scene_bvh(scene));
     printf("Scene + BVH construction took: %fs\n", std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count());
 
-    CHECK(bpt_set_sampler_tables(ctx, blob.data(), blob.data() + 16384, blob.data() + 81920, blob.data() + 212992));
-    CHECK(bpt_upload_scene(ctx, scene));
-    CHECK(bpt_film_resize(ctx, w, h));
-    t0 = std::chrono::steady_clock::now();
-    for (uint32_t p = 0; p < passes; ++p) CHECK(bpt_render_pass(ctx, 0, 0, (int32_t)w, (int32_t)h, p*spp, spp, BPT_SEED_PER_PIXEL, p));
-    CHECK(bpt_sync(ctx));
-    double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
-    bpt_stats st;
-    CHECK(bpt_get_stats(ctx, &st, 0));
-    printf("Took %ux%u %uspp image in %f seconds.  (%.1f Mrays/s, %.1f Msamples/s)\n", w, h, spp*passes, sec,
-           (double)st.rays/sec/1e6, (double)st.samples/sec/1e6);
-
     bpt_post_settings post = {0.0f, 1, 1, 0.5f, 0.0f};      // init_scene defaults (raytracer.cpp:1450-1452)
     std::vector<uint32_t> pixels((size_t)w*h);
-    CHECK(bpt_resolve_bgra8(ctx, &post, nullptr, 0, 0, pixels.data()));
+    if (gpus > 1) {
+        // one host thread + one context per GPU (devices device .. device+gpus-1), ncclCommInitAll, reduce to rank 0
+        bpt_destroy(ctx); ctx = nullptr;
+        std::vector<int> devs(gpus);
+        for (int i = 0; i < gpus; ++i) devs[i] = device + i;
+        std::vector<void*> comms(gpus, nullptr);
+        CHECK(bpt_nccl_comm_init_all(gpus, devs.data(), comms.data()));
+        std::vector<bpt_ctx*> ctxs(gpus, nullptr);
+        std::vector<bpt_stats> stats(gpus);
+        std::vector<int> rcs(gpus, 0);
+        std::vector<std::thread> threads;
+        t0 = std::chrono::steady_clock::now();
+        for (int r = 0; r < gpus; ++r)
+            threads.emplace_back([&, r]() {
+                rcs[r] = render_rank(r, gpus, devs[r], comms[r], scene, blob.data(), w, h, spp, passes, &ctxs[r], &stats[r]);
+                if (rcs[r]) { fprintf(stderr, "GPU %d failed; aborting (the other ranks would wait in the collective)\n", devs[r]); _Exit(1); }
+            });
+        for (auto& t : threads) t.join();
+        double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        uint64_t rays = 0, samples = 0;
+        for (int r = 0; r < gpus; ++r) { rays += stats[r].rays; samples += stats[r].samples; }
+        printf("Took %ux%u %uspp image in %f seconds on %d GPUs incl. context setup and scene upload.  (%.1f Mrays/s, %.1f Msamples/s)\n",
+               w, h, spp*passes, sec, gpus, (double)rays/sec/1e6, (double)samples/sec/1e6);
+        CHECK(bpt_resolve_reduced_bgra8(ctxs[0], &post, nullptr, 0, 0, pixels.data()));
+        for (int r = 0; r < gpus; ++r) { bpt_nccl_comm_destroy(comms[r]); bpt_destroy(ctxs[r]); }
+    } else {
+        CHECK(bpt_set_sampler_tables(ctx, blob.data(), blob.data() + 16384, blob.data() + 81920, blob.data() + 212992));
+        CHECK(bpt_upload_scene(ctx, scene));
+        CHECK(bpt_film_resize(ctx, w, h));
+        t0 = std::chrono::steady_clock::now();
+        for (uint32_t p = 0; p < passes; ++p) CHECK(bpt_render_pass(ctx, 0, 0, (int32_t)w, (int32_t)h, p*spp, spp, BPT_SEED_PER_PIXEL, p));
+        CHECK(bpt_sync(ctx));
+        double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        bpt_stats st;
+        CHECK(bpt_get_stats(ctx, &st, 0));
+        printf("Took %ux%u %uspp image in %f seconds.  (%.1f Mrays/s, %.1f Msamples/s)\n", w, h, spp*passes, sec,
+               (double)st.rays/sec/1e6, (double)st.samples/sec/1e6);
+        CHECK(bpt_resolve_bgra8(ctx, &post, nullptr, 0, 0, pixels.data()));
+        bpt_destroy(ctx);
+    }
     CHECK(bpt_write_bitmap(out, pixels.data(), w, h));
     printf("wrote %s\n", out);
-    bpt_destroy(ctx);
     bpt_scene_destroy(scene);
     return 0;
 }

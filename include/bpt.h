@@ -240,6 +240,13 @@ BPT_API int bpt_get_scene_bvh(const bpt_scene* s, const bpt_bvh_node** nodes, ui
 BPT_API int bpt_get_mesh_bvh(const bpt_scene* s, uint32_t mesh, const bpt_bvh_node** nodes, uint32_t* node_count,
                              const uint32_t** indices, uint32_t* index_count,
                              const float** leaf_order_triangles /* 9 floats each */);
+/* The same trees in the layout the device traverses (csrc/wide_bvh.h: 64-byte sibling pairs grouped into two-level
+ * records; every child carries the reference node's box verbatim plus a packed reference).  mesh < 0 selects the TLAS.
+ * pairs points at 2*pair_count children; big_leaves at big_leaf_count {first, count} pairs.  Read-only, for parity checks
+ * of the re-layout (tests/test_wide_layout.py decodes it back into the reference node array). */
+typedef struct bpt_wide_child { float bv_p[3]; float bv_r[3]; uint32_t ref; uint32_t aux; } bpt_wide_child;
+BPT_API int bpt_get_wide_bvh(const bpt_scene* s, int32_t mesh, const bpt_wide_child** pairs, uint32_t* pair_count,
+                             bpt_wide_child* root, const uint32_t** big_leaves, uint32_t* big_leaf_count, uint32_t* depth);
 /* ---- asset readers: the reference's parse_obj (Raytracer/assets.cpp:187-400) and parse_hdr (:411-600),
  * same input -> same triangles / texels, quirks included (see csrc/obj_hdr_readers.cpp).  Malformed input that would make the
  * reference read out of bounds or loop forever returns an error here. */
@@ -363,6 +370,33 @@ BPT_API int bpt_set_tail_threshold(bpt_ctx* ctx, uint32_t paths);
 BPT_API int bpt_build_mesh_bvh_device(bpt_ctx* ctx, uint32_t triangle_count, const float* positions,
                                       int32_t method /* BPT_BVH_SAH_BINNED or BPT_BVH_MIDPOINT_SPLIT */, bpt_bvh_node* nodes_out, uint32_t node_capacity, uint32_t* node_count,
                                       uint32_t* indices_out, float* build_ms);
+
+/* ---------------------------------------------------------------------------------
+ * 3. Multi-GPU: the image is split into row bands over the GPUs of one box, the scene is replicated, every
+ *    rank accumulates its bands (plus the filter's halo rows) into its own full-frame film, and ONE NCCL reduce per
+ *    progressive pass sums the partial films on the root.  The reference's analogue is its worker threads sharing one
+ *    AccumulationBuffer (raytracer.cpp:551-603); (sum w*rgb, sum w) is linear, so the sum of the partial films is the
+ *    single-GPU film up to float-add order.  One context per GPU; one host thread (or process) per context.
+ *    NCCL (libnccl.so.2) is loaded on first use of these entry points; the rest of the library does not need it.
+ * ------------------------------------------------------------------------------- */
+typedef struct bpt_nccl_id { char internal[128]; } bpt_nccl_id;               /* ncclUniqueId */
+BPT_API int bpt_nccl_get_unique_id(bpt_nccl_id* out);                         /* rank 0 calls this and hands the id to the others */
+/* ncclCommInitRank on the context's device; *out_comm is an ncclComm_t (usable with NCCL directly). */
+BPT_API int bpt_nccl_comm_init_rank(bpt_ctx* ctx, const bpt_nccl_id* id, int nranks, int rank, void** out_comm);
+/* ncclCommInitAll: one process driving ndev devices (the headless driver's --gpus N); out_comms[ndev]. */
+BPT_API int bpt_nccl_comm_init_all(int ndev, const int* devices, void** out_comms);
+BPT_API int bpt_nccl_comm_destroy(void* comm);
+/* reduced film (root only) := sum over ranks of the ranks' films; enqueued on the context's stream behind the passes
+ * rendered so far, no host synchronisation.  The partial films are NOT modified, so progressive passes keep accumulating
+ * into them and the next bpt_reduce_film gives the sum of everything rendered so far (no double counting).
+ * `nccl_comm` is an ncclComm_t (from bpt_nccl_comm_init_* or the caller's own NCCL of the same process).
+ * Every rank of the communicator must make the call (it is a collective). */
+BPT_API int bpt_reduce_film(bpt_ctx* ctx, void* nccl_comm, int root);
+BPT_API int bpt_reduced_film_device_ptr(bpt_ctx* ctx, void** out_device_ptr); /* root: valid after the first bpt_reduce_film */
+BPT_API int bpt_download_reduced_film(bpt_ctx* ctx, float* out_rgba /* w*h*4 floats, host */);
+/* bpt_resolve_bgra8 on the root's reduced film */
+BPT_API int bpt_resolve_reduced_bgra8(bpt_ctx* ctx, const bpt_post_settings* post, const uint8_t* dither_rgb8,
+                                      uint32_t dither_w, uint32_t dither_h, uint32_t* out_pixels);
 
 /* cumulative bytes this context copied host->device / device->host (scene uploads, rays, film, records) */
 BPT_API int bpt_get_transfer_bytes(bpt_ctx* ctx, uint64_t* h2d, uint64_t* d2h, int reset);

@@ -99,3 +99,30 @@ def test_product_tlas_matches_golden_hash(bpt, golden, name):
     recipe(s, w, h, **kw)
     n, i = s.scene_bvh()
     assert hashlib.sha256(n.tobytes() + i.tobytes()).digest() == golden[f"{name}_tlas_sha"].tobytes()
+
+
+def test_standalone_inputs_library_matches_the_product(bpt):
+    """oracle/_ref/libbpt_inputs.so is the product's procedural_inputs.cpp built standalone (the reference arm of bench.py
+    builds its scenes from it without loading libbpt.so): same bytes"""
+    from oracle import ref_inputs
+    from buas_pathtracer_b200 import lib
+    for level in (0, 2, 5):
+        a, b = ref_inputs.make_displaced_icosphere(level), lib.make_displaced_icosphere(level)
+        assert a.shape == b.shape and np.array_equal(a.view(np.uint32), b.view(np.uint32))
+    a, b = ref_inputs.make_procedural_skydome(128, 64), lib.make_procedural_skydome(128, 64)
+    assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+
+
+def test_reference_arm_of_bench_never_loads_the_product_library():
+    """bench.py --impl reference must run with the product library absent (BENCH `reference.native_so_loaded`)"""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, BPT_LIBRARY="/nonexistent/libbpt.so")
+    p = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--config", "c1",
+                        "--steps", "1", "--warmup", "0"], env=env, capture_output=True, text=True, timeout=300)
+    assert p.returncode == 0, p.stderr[-2000:]
+    line = json.loads(p.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["value"] > 0 and line["cpu_baseline"]["kind"] == "reference"
+    assert line["config"]["spp_per_step_run"] >= 1 and 1.0 < line["rays_per_sample"] < 12.0
