@@ -152,7 +152,7 @@ int ensure_state(bpt_ctx* ctx, bpt_ctx::Pipe* pp, uint32_t slots) {
     rc |= alloc((void**)&pp->st.prev_n, n*16);
     rc |= alloc((void**)&pp->st.jitter, n*8);
     rc |= alloc((void**)&pp->st.mstack_at, n);
-    rc |= alloc((void**)&pp->st.mstack, n*2*BPT_MATERIAL_STACK_DEPTH);
+    rc |= alloc((void**)&pp->st.mstack, n*2*(BPT_MATERIAL_STACK_DEPTH - 1));     // level 0 ("air") is implicit
     rc |= alloc((void**)&pp->st.primary_d, n*16);
     rc |= alloc((void**)&pp->st.primary_o, n*16);
     rc |= alloc((void**)&pp->q.active[0], n*4);

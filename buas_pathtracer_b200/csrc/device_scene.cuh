@@ -102,13 +102,13 @@ struct DPathState {
     float4*   ray_d;        // {d.xyz, unused}
     float4*   hit;          // {t, prim (bits), tri slot (bits), v}
     float*    hit_w;        // barycentric w
-    float4*   throughput;   // {xyz, vignette}
-    float4*   radiance;     // {total_color.xyz, unused}
+    float4*   throughput;   // {xyz, unused}
+    float4*   radiance;     // {total_color.xyz, vignette}  (first written by the first bounce's shading)
     uint4*    rng;          // RandomSeries (samplers.h:29-34)
     float4*   prev_n;       // {prev_N.xyz, bits: flags}   flags: bit0 = is_specular_bounce
     float2*   jitter;       // AA jitter (raytracer.cpp:444-446)
     uint8_t*  mstack_at;    // material_stack_at
-    uint16_t* mstack;       // [64][slots] level-major material ids
+    uint16_t* mstack;       // [63][slots] level-major material ids of stack levels 1..63 (level 0 is always the integrator's "air")
     float4*   primary_d;    // {primary ray d.xyz, ray count} (records / vignette)
     float4*   primary_o;    // only written when records are requested
 };

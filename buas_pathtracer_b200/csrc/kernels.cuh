@@ -212,6 +212,27 @@ BPT_D void hit_geometry(const DScene& sc, V3 ro, V3 rd, const HitRecord& h, V3& 
     N = noz(xform_normal(m, n));
 }
 
+// the per-sample RandomSeries as k_raygen leaves it: seeded per pixel and sample, advanced by the AA and the
+// DOF draw (every get_next_sample_* call advances the series exactly once, samplers.h:36-45)
+BPT_D uint4 primary_rng_state(const SamplerCtx& sm, const BatchDesc& b) {
+    uint4 rng = random_seed(hash_coordinate3(sm.x, sm.y, sm.index) ^ b.salt);
+    next_set(rng); next_set(rng);
+    return rng;
+}
+
+// raytracer.cpp:469-474
+BPT_D float primary_vignette(const DScene& sc, V3 ray_d) {
+    float vignette = dot(ray_d, v3(sc.camera.z));
+    vignette = vignette*vignette*vignette*vignette;
+    return lerp_f(1.0f, vignette, sc.settings.vignette_strength);
+}
+
+// material_stack[level] of a path: level 0 is always the integrator's local "air" (integrators.cpp:597-600) and is not
+// stored; level L >= 1 lives in plane L-1 of DPathState::mstack
+BPT_D uint32_t mstack_get(const DScene& sc, const DPathState& st, const BatchDesc& b, uint32_t slot, int level) {
+    return level <= 0 ? sc.air_material : (uint32_t)st.mstack[(size_t)(level - 1)*b.slots + slot];
+}
+
 // ---- kernels ---------------------------------------------------------------------------------------------------------------
 
 // render_tile's per-sample ray setup (raytracer.cpp:372-461) with per-pixel counter-based seeding
@@ -247,19 +268,13 @@ k_raygen(DScene sc, DPathState st, BatchDesc b) {
         V3 ray_o = lens_p;
         V3 ray_d = normalize(film_p - lens_p);
 
-        float vignette = dot(ray_d, cam_z);
-        vignette = vignette*vignette*vignette*vignette;
-        vignette = lerp_f(1.0f, vignette, sc.settings.vignette_strength);
-
         st.ray_o[slot] = make_float4(ray_o.x, ray_o.y, ray_o.z, 3.402823466e+38f);    // make_ray's FLT_MAX far clip
         st.ray_d[slot] = make_float4(ray_d.x, ray_d.y, ray_d.z, 0.0f);
-        st.throughput[slot] = make_float4(1.0f, 1.0f, 1.0f, vignette);
-        // radiance (= 0), prev_n (= none, "specular") and material_stack_at (= 0) are what IntegratorState starts with
-        // (integrators.cpp:587-600): the first bounce's shading knows them, so they are not written here nor read there
-        // (49 of 139 bytes per sample; raygen and the first shade are HBM-bound)
-        st.rng[slot] = rng;
         st.jitter[slot] = make_float2(jx, jy);
-        st.mstack[slot] = (uint16_t)sc.air_material;                                    // material_stack[0] = &air
+        // Everything else IntegratorState starts with (integrators.cpp:587-600) is a function of the slot, so the first
+        // bounce's shading re-derives it instead of reading it back from HBM: throughput = 1, radiance = 0, no previous
+        // normal ("specular"), material stack = {air}, the RNG state = this seed advanced by the two draws above
+        // (primary_rng_state), the vignette = primary_vignette(ray_d).  40 of 139 bytes per sample are written here.
         if (b.want_records) {
             st.primary_d[slot] = make_float4(ray_d.x, ray_d.y, ray_d.z, 0.0f);
             st.primary_o[slot] = make_float4(ray_o.x, ray_o.y, ray_o.z, 0.0f);
@@ -292,7 +307,7 @@ BPT_D void flush_ray_counts(DStats* stats, uint32_t rays, uint32_t shadow) {
 }
 
 #ifndef BPT_TRACE_MIN_CTAS
-#define BPT_TRACE_MIN_CTAS 8      // 64 registers: +3.4 % on C2 over 7 CTAs/72 registers (latency-bound: more resident warps win); 9 and 10 CTAs lose to spills
+#define BPT_TRACE_MIN_CTAS 9      // 56 registers, no spills since the per-ray state moved to shared memory: traversal 43.7 ms on C2 against 45.0 at 8 CTAs; 10 CTAs (51 registers) spill and lose (47 ms)
 #endif
 
 struct ClosestSrc {        // rays come from the path state (through the active queue), hits go back to it
@@ -409,9 +424,10 @@ BPT_D void shade_path_simple(const DScene& sc, const DPathState& st, const Batch
     V3 ro = v3(ro4), rd = v3(rd4);
     HitRecord h;
     h.t = h4.x; h.prim = __float_as_uint(h4.y); h.tri = __float_as_uint(h4.z); h.v = h4.w; h.w = sc.normals ? st.hit_w[slot] : 0.0f;
-    float4 tp4 = st.throughput[slot];
-    V3 throughput = v3(tp4);
-    V3 total = bounce == 0 ? v3(0.0f) : v3(st.radiance[slot]);
+    const bool first = bounce == 0;                       // state the ray generation did not write (see k_raygen)
+    V3 throughput = first ? v3(1.0f) : v3(st.throughput[slot]);
+    float4 rad4 = first ? make_float4(0.0f, 0.0f, 0.0f, primary_vignette(sc, rd)) : st.radiance[slot];   // .w carries the vignette to the splat
+    V3 total = v3(rad4);
     if (b.want_records) { float4 pd = st.primary_d[slot]; pd.w = __uint_as_float(__float_as_uint(pd.w) + 1u); st.primary_d[slot] = pd; }
     alive = false;
 
@@ -431,7 +447,7 @@ BPT_D void shade_path_simple(const DScene& sc, const DPathState& st, const Batch
             if (m.flags & BPT_MATERIAL_EMISSIVE) {
                 total = total + throughput*m.emission;                                                           // :505-508
             } else {
-                uint4 rng = st.rng[slot];
+                uint4 rng = first ? primary_rng_state(make_sampler(sc, b, slot), b) : st.rng[slot];
                 next_set(rng);                                                                                   // random_unilaterals :510
                 float rx = unilateral(rng.x);
                 V2 ryz; ryz.x = unilateral(rng.y); ryz.y = unilateral(rng.z);
@@ -462,13 +478,13 @@ BPT_D void shade_path_simple(const DScene& sc, const DPathState& st, const Batch
                     st.ray_o[slot] = make_float4(next_o.x, next_o.y, next_o.z, 3.402823466e+38f);
                     st.ray_d[slot] = make_float4(next_d.x, next_d.y, next_d.z, 0.0f);
                     st.rng[slot] = rng;
-                    st.throughput[slot] = make_float4(throughput.x, throughput.y, throughput.z, tp4.w);
+                    st.throughput[slot] = make_float4(throughput.x, throughput.y, throughput.z, 0.0f);
                     octant = direction_octant(next_d);
                 }
             }
         }
     }
-    st.radiance[slot] = make_float4(total.x, total.y, total.z, 0.0f);
+    st.radiance[slot] = make_float4(total.x, total.y, total.z, rad4.w);
 }
 
 // One bounce of advanced_integrator (integrators.cpp:612-818) for ONE path: reads the path's state and the hit of its
@@ -482,10 +498,10 @@ BPT_D void shade_path(const DScene& sc, const DPathState& st, const BatchDesc& b
     V3 ro = v3(ro4), rd = v3(rd4);
     HitRecord h;
     h.t = h4.x; h.prim = __float_as_uint(h4.y); h.tri = __float_as_uint(h4.z); h.v = h4.w; h.w = sc.normals ? st.hit_w[slot] : 0.0f;
-    float4 tp4 = st.throughput[slot];
-    V3 throughput = v3(tp4);
     const bool first = bounce == 0;                       // state the ray generation did not write (see k_raygen)
-    V3 total = first ? v3(0.0f) : v3(st.radiance[slot]);
+    V3 throughput = first ? v3(1.0f) : v3(st.throughput[slot]);
+    float4 rad4 = first ? make_float4(0.0f, 0.0f, 0.0f, primary_vignette(sc, rd)) : st.radiance[slot];   // .w carries the vignette to the splat
+    V3 total = v3(rad4);
     float4 pd = make_float4(0, 0, 0, 0);
     if (b.want_records) pd = st.primary_d[slot];
     uint32_t ray_count = __float_as_uint(pd.w) + 1u;      // this bounce's intersect_scene call
@@ -496,7 +512,7 @@ BPT_D void shade_path(const DScene& sc, const DPathState& st, const BatchDesc& b
         total_changed = true;
     } else {
         SamplerCtx sm = make_sampler(sc, b, slot);
-        uint4 rng = st.rng[slot];
+        uint4 rng = first ? primary_rng_state(sm, b) : st.rng[slot];
         float4 pn4 = first ? make_float4(0.0f, 0.0f, 0.0f, __uint_as_float(1u)) : st.prev_n[slot];   // is_specular_bounce starts true
         V3 prev_N = v3(pn4);
         bool is_specular = (__float_as_uint(pn4.w) & 1u) != 0;
@@ -513,11 +529,11 @@ BPT_D void shade_path(const DScene& sc, const DPathState& st, const BatchDesc& b
         if (inside) {
             id_i = surface_id;
             int below = stack_at - 1; if (below < 0) below = 0;
-            id_t = st.mstack[(size_t)below*b.slots + slot];
+            id_t = mstack_get(sc, st, b, slot, below);
             cos_i = -cos_i;
             N = -N;
         } else {
-            id_i = st.mstack[(size_t)stack_at*b.slots + slot];
+            id_i = mstack_get(sc, st, b, slot, stack_at);
             id_t = surface_id;
         }
         MatView mi = load_material(sc, id_i);
@@ -570,7 +586,7 @@ BPT_D void shade_path(const DScene& sc, const DPathState& st, const BatchDesc& b
                     if (stack_at > 0) --stack_at;
                 } else if (stack_at < (BPT_MATERIAL_STACK_DEPTH - 1)) {
                     ++stack_at;
-                    st.mstack[(size_t)stack_at*b.slots + slot] = (uint16_t)id_t;
+                    st.mstack[(size_t)(stack_at - 1)*b.slots + slot] = (uint16_t)id_t;
                 }
                 V3 refr = ratio*rd + N*(ratio*cos_i - cos_t);
                 next_o = I + refr*kEps; next_d = refr;
@@ -693,12 +709,12 @@ BPT_D void shade_path(const DScene& sc, const DPathState& st, const BatchDesc& b
                 st.rng[slot] = rng;
                 st.prev_n[slot] = make_float4(N.x, N.y, N.z, __uint_as_float(is_specular ? 1u : 0u));
                 st.mstack_at[slot] = (uint8_t)stack_at;
-                st.throughput[slot] = make_float4(throughput.x, throughput.y, throughput.z, tp4.w);
+                st.throughput[slot] = make_float4(throughput.x, throughput.y, throughput.z, 0.0f);
                 octant = direction_octant(next_d);
             }
         }
     }
-    if (total_changed || first) st.radiance[slot] = make_float4(total.x, total.y, total.z, 0.0f);
+    if (total_changed || first) st.radiance[slot] = make_float4(total.x, total.y, total.z, rad4.w);
     if (b.want_records) { pd.w = __uint_as_float(ray_count); st.primary_d[slot] = pd; }
 }
 
@@ -910,7 +926,7 @@ k_splat(DScene sc, DPathState st, BatchDesc b, float4* __restrict__ film) {
         for (uint32_t s = 0; s < b.S; ++s) {
             uint32_t slot = pix*b.S + s;
             float4 rad = st.radiance[slot];
-            float vig = st.throughput[slot].w;
+            float vig = rad.w;
             float2 j = st.jitter[slot];
             V3 c = v3(rad)*vig;
             float wx[SPAN], wy[SPAN];
@@ -953,7 +969,7 @@ k_splat_generic(DScene sc, DPathState st, BatchDesc b, float4* __restrict__ film
         uint32_t pix = slot / b.S;
         int x = b.x0 + (int)(pix % b.rect_w), y = __ldg(&b.row_map[b.row0 + pix / b.rect_w]);
         float4 rad = st.radiance[slot];
-        float vig = st.throughput[slot].w;
+        float vig = rad.w;
         V3 c = v3(rad)*vig;
         if (sc.filter_lut_size == 0) {
             atomicAdd(&film[(size_t)y*sc.film_w + x], make_float4(c.x, c.y, c.z, 1.0f));

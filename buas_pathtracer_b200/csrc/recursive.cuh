@@ -58,7 +58,7 @@ struct RecursiveSrc {
         prev_mat = NO_MATERIAL;
         if (valid) {
             sm = make_sampler(scene, batch, s);
-            rng = st.rng[s];
+            rng = primary_rng_state(sm, batch);             // k_raygen leaves everything but the ray to its consumers
             ray_o = v3(st.ray_o[s]); ray_d = v3(st.ray_d[s]);
         }
     }
@@ -237,7 +237,7 @@ struct RecursiveSrc {
             }
             case ST_RETURN: {
                 if (depth == 0) {
-                    st.radiance[slot] = make_float4(value.x, value.y, value.z, 0.0f);
+                    st.radiance[slot] = make_float4(value.x, value.y, value.z, primary_vignette(*sc, v3(st.ray_d[slot])));   // .w: vignette for the splat
                     if (b->want_records) { float4 pd = st.primary_d[slot]; pd.w = __uint_as_float(n_rays); st.primary_d[slot] = pd; }
                     state = ST_DONE;
                     return false;

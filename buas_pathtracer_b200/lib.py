@@ -238,6 +238,15 @@ def make_procedural_skydome(w=2048, h=1024):
     return px
 
 
+def nccl_comm_init_all(devices):
+    """ncclCommInitAll for one process driving several GPUs: a list of ncclComm_t handles, one per device"""
+    L = load_library()
+    devs = (C.c_int * len(devices))(*devices)
+    comms = (C.c_void_p * len(devices))()
+    _check(L.bpt_nccl_comm_init_all(len(devices), devs, comms), "bpt_nccl_comm_init_all")
+    return [C.c_void_p(c) for c in comms]
+
+
 class Renderer:
     """One GPU context (one per process/GPU).  Raises BptError when no CUDA device is usable."""
 

@@ -74,6 +74,14 @@ BPT_API int ref_render_parity(ref_scene* s, float* film, uint32_t w, uint32_t h,
 BPT_API int ref_render_threaded(ref_scene* s, uint32_t w, uint32_t h, uint32_t spp, uint32_t threads,
                                 float* film, double* seconds, bpt_stats* stats);
 
+/* The reference's display-loop resolve (raytracer.cpp:2103-2173: /w, exposure, 1-exp(-x), gamma, sigmoidal contrast, TPDF
+ * blue-noise dither, BGRA8 pack), compiled from the reference's own text (oracle/tools/slice_resolve.py cuts the loop out
+ * of raytracer.cpp at build time), and its write_bitmap (assets.cpp:693-724).  dither_rgb8: a power-of-two RGB8 tile
+ * (the reference always dithers; there is no NULL path). */
+BPT_API int ref_resolve_bgra8(const float* film_rgba, uint32_t w, uint32_t h, const bpt_post_settings* post,
+                              const uint8_t* dither_rgb8, uint32_t dither_w, uint32_t dither_h, uint32_t* out_pixels);
+BPT_API int ref_write_bitmap(const char* file_name, const uint32_t* pixels, uint32_t w, uint32_t h);
+
 /* The reference's own parse_obj / parse_hdr (assets.cpp:187-400, :423-600).  Two-call pattern: NULL outputs = report sizes. */
 BPT_API int ref_parse_obj(const char* text, int winding, uint32_t* triangle_count, int* has_normals, int* has_texcoords,
                           float* positions, float* normals, float* texcoords);

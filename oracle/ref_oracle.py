@@ -129,6 +129,34 @@ def sizeof(name):
     return lib().ref_sizeof(name.encode())
 
 
+def resolve_bgra8(film, exposure=0.0, tonemapping=True, srgb_transform=True, midpoint=0.5, contrast=0.0, dither=None):
+    """the reference's display-loop resolve (raytracer.cpp:2103-2173, its own text compiled into the oracle): film (h, w, 4)
+    float32 -> (h, w) uint32 0xAARRGGBB.  The reference always dithers: `dither` is a power-of-two (dh, dw, 3) uint8 tile."""
+    L = lib()
+    L.ref_resolve_bgra8.restype = C.c_int
+    L.ref_resolve_bgra8.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.POINTER(capi.PostSettings), C.c_void_p, C.c_uint32,
+                                    C.c_uint32, C.c_void_p]
+    film = np.ascontiguousarray(film, np.float32)
+    h, w, _ = film.shape
+    dither = np.ascontiguousarray(dither, np.uint8)
+    dh, dw, _ = dither.shape
+    post = capi.PostSettings(exposure, int(tonemapping), int(srgb_transform), midpoint, contrast)
+    out = np.empty((h, w), np.uint32)
+    rc = L.ref_resolve_bgra8(film.ctypes.data, w, h, C.byref(post), dither.ctypes.data, dw, dh, out.ctypes.data)
+    assert rc == 0
+    return out
+
+
+def write_bitmap(path, pixels):
+    """the reference's write_bitmap (assets.cpp:693-724) on a (h, w) uint32 array"""
+    L = lib()
+    L.ref_write_bitmap.restype = C.c_int
+    L.ref_write_bitmap.argtypes = [C.c_char_p, C.c_void_p, C.c_uint32, C.c_uint32]
+    px = np.ascontiguousarray(pixels, np.uint32)
+    h, w = px.shape
+    assert L.ref_write_bitmap(path.encode(), px.ctypes.data, w, h) == 0
+
+
 def parse_obj(text, winding=1):
     """the reference's parse_obj (assets.cpp:187-400): (positions, normals|None, texcoords|None) as (n, 9) arrays, or None on a parse error"""
     L = lib()

@@ -1,8 +1,9 @@
 """ORACLE-ONLY (test infrastructure), kind "port": numpy restatement of the reference's display-loop resolve
-(Raytracer/raytracer.cpp:2103-2172) and BMP header (assets.cpp:671-724).  The reference code sits inside SDL_main and
-cannot be called headless, so this row is checked against a port -- **parity unpinned** by any
-reference golden vector (the reference has none for it); exp/pow go through numpy's float32 routines, and remap_tpdf's
-SSE rsqrt approximation (my_math.h:50-54) is replaced by an exact 1/sqrt, so the stated tolerance is +-1 LSB."""
+(Raytracer/raytracer.cpp:2103-2172) and BMP header (assets.cpp:671-724).  Since round 2 the reference's own resolve loop
+is compiled into oracle/_ref (oracle/tools/slice_resolve.py) and tests/test_resolve.py compares the device kernel with THAT;
+this port is pinned against it there (tests/test_resolve.py::test_resolve_port_agrees_with_the_references_resolve) and is
+only still used for the one path the reference does not have: resolving without a dither tile.  exp/pow go through numpy's
+float32 routines, and remap_tpdf's SSE rsqrt approximation (my_math.h:50-54) is replaced by an exact 1/sqrt: +-1 LSB."""
 import struct
 
 import numpy as np

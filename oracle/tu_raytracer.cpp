@@ -356,6 +356,38 @@ BPT_API int ref_render_threaded(ref_scene* s, uint32_t w, uint32_t h, uint32_t s
     return 0;
 }
 
+// The reference's display-loop resolve.  The loop below is the reference's OWN text, cut out of raytracer.cpp:2103-2173
+// at build time (oracle/tools/slice_resolve.py -> oracle/_ref/resolve_slice.inc, generated and git-ignored); the locals
+// here only give it the names it uses inside SDL_main.
+BPT_API int ref_resolve_bgra8(const float* film_rgba, uint32_t w_, uint32_t h_, const bpt_post_settings* post,
+                              const uint8_t* dither_rgb8, uint32_t dither_w, uint32_t dither_h, uint32_t* out_pixels) {
+    if (!film_rgba || !post || !dither_rgb8 || !out_pixels || dither_w == 0 || dither_h == 0) return -1;
+    AccumulationBuffer buffer = {};
+    buffer.w = w_; buffer.h = h_; buffer.pixels = (V4*)film_rgba;
+    AccumulationBuffer* hdr_buffer = &buffer;
+    PostProcessSettings settings_copy;
+    settings_copy.exposure = post->exposure; settings_copy.tonemapping = post->tonemapping;
+    settings_copy.srgb_transform = post->srgb_transform; settings_copy.midpoint = post->midpoint; settings_copy.contrast = post->contrast;
+    PostProcessSettings* post_settings = &settings_copy;
+    Image_R8G8B8 noise = {};
+    noise.w = dither_w; noise.h = dither_h; noise.pixels = (Color_R8G8B8*)dither_rgb8;
+    Image_R8G8B8* dither_noise = &noise;
+    void* pixels = out_pixels;
+    int w = (int)w_, h = (int)h_;
+    {
+#include "resolve_slice.inc"
+    }
+    return 0;
+}
+
+// write_bitmap (assets.cpp:693-724), the reference's own
+BPT_API int ref_write_bitmap(const char* file_name, const uint32_t* pixels, uint32_t w, uint32_t h) {
+    ensure_platform();
+    static Arena arena = {};
+    write_bitmap((u32*)pixels, w, h, file_name, &arena);
+    return 0;
+}
+
 } // extern "C"
 
 // ---- the reference's asset parsers (assets.cpp, compiled unmodified into assets.o) ---------------------------------
