@@ -39,19 +39,37 @@ struct bpt_ctx {
     int trace_ctas_per_sm = 8;            // resident CTAs of the persistent traversal kernels (occupancy query)
     cudaStream_t stream = nullptr;
 
-    DScene sc{};
+    DScene sc{};                          // what the next pass renders: the active scene set + latched camera / settings
     bool scene_ready = false;
     bool tables_ready = false;
-    std::vector<void*> scene_allocs;      // (unused, kept for destroy)
-    struct Slot { void* p = nullptr; size_t cap = 0; } slots[SL_COUNT];   // grow-only device buffers of the uploaded scene
-    char* staging = nullptr;              // pinned host block for the small flattened tables
-    size_t staging_capacity = 0;
-    uint32_t* tri_original = nullptr;     // DTriangle slot -> original triangle index (MeshBVH::indices)
+    struct Slot { void* p = nullptr; size_t cap = 0; };
+    // The uploaded scene is double-buffered: bpt_upload_scene_async fills the set that is not being rendered, on a copy
+    // stream, while passes over the active set are still running; the next pass flips to it.
+    struct SceneSet {
+        Slot slots[SL_COUNT];             // grow-only device buffers
+        char* staging = nullptr;          // pinned host block for the small flattened tables
+        size_t staging_capacity = 0;
+        float* d_filter = nullptr;        // the reconstruction-filter LUT latched with this upload
+        uint32_t* tri_original = nullptr; // DTriangle slot -> original triangle index (MeshBVH::indices)
+        uint32_t stack_bound = 0;
+        cudaEvent_t last_use = nullptr;   // behind the last pass / trace enqueued that reads this set
+        cudaEvent_t uploaded = nullptr;   // behind the last upload into this set (the staging block is free again)
+        bool used = false, staged = false;
+    } sets[2];
+    int active_set = 0;
+    bool pending = false;                 // an uploaded scene waits in sets[1 - active_set] for the next pass to flip to it
+    DScene pending_sc{};
+    cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
+    Slot misc_slots[SL_COUNT];            // bpt_trace / bpt_resolve scratch (not part of a scene)
+    uint32_t* tri_original = nullptr;     // of the active set
+    float4* film_front = nullptr;         // snapshot of the film a bpt_download_film_async copies out from (the reference's front buffer, raytracer.cpp:705-709)
+    uint32_t film_front_w = 0, film_front_h = 0;
+    cudaEvent_t front_ready = nullptr, download_done = nullptr;
+    bool download_pending = false;
 
     uint8_t *d_perm = nullptr, *d_sobol = nullptr, *d_scramble = nullptr, *d_rank = nullptr;
-    float* d_filter = nullptr;
 
-    uint32_t stack_bound = 0;             // TLAS depth + deepest BLAS of the uploaded scene: most stack entries one ray can have pending
+    uint32_t stack_bound = 0;             // TLAS depth + deepest BLAS of the active scene: most stack entries one ray can have pending
 
     float4* film = nullptr;
     float4* film_reduced = nullptr;       // root of a multi-GPU job: sum of all ranks' films (bpt_reduce_film)
@@ -112,8 +130,8 @@ int upload(bpt_ctx* ctx, const T* host, size_t count, const T** out, std::vector
     return BPT_OK;
 }
 
-int device_slot(bpt_ctx* ctx, int id, size_t bytes, void** out) {
-    bpt_ctx::Slot& sl = ctx->slots[id];
+int device_slot(bpt_ctx::Slot* slots, int id, size_t bytes, void** out) {
+    bpt_ctx::Slot& sl = slots[id];
     bytes = std::max<size_t>(bytes, 256);
     if (sl.cap < bytes) {
         if (sl.p) cudaFree(sl.p);
@@ -201,17 +219,42 @@ void fill_rows(float4* dst, const bpt_m4x4& m) {
     for (int r = 0; r < 3; ++r) dst[r] = make_float4(m.e[r][0], m.e[r][1], m.e[r][2], m.e[r][3]);
 }
 
-void latch_settings(bpt_ctx* ctx, const bpt_scene* scene) {
+void latch_settings(DScene* sc, const bpt_scene* scene) {
     // what render_all_tiles does when a render (re)starts (raytracer.cpp:711-720)
     bpt_camera cam = scene->new_camera;
     recompute_camera(&cam);
-    ctx->sc.camera = cam;
-    ctx->sc.settings = scene->new_settings;
-    ctx->sc.filter_radius = scene->filter.kernel_size;
-    ctx->sc.filter_lut_size = scene->filter.cache_size;
-    memcpy(ctx->sc.top_sky, scene->top_sky_color, 12);
-    memcpy(ctx->sc.bot_sky, scene->bot_sky_color, 12);
-    memcpy(ctx->sc.ambient_light, scene->ambient_light, 12);
+    sc->camera = cam;
+    sc->settings = scene->new_settings;
+    sc->filter_radius = scene->filter.kernel_size;
+    sc->filter_lut_size = scene->filter.cache_size;
+    memcpy(sc->top_sky, scene->top_sky_color, 12);
+    memcpy(sc->bot_sky, scene->bot_sky_color, 12);
+    memcpy(sc->ambient_light, scene->ambient_light, 12);
+}
+
+// the next pass (or trace) is about to be enqueued: switch to a scene that bpt_upload_scene_async left waiting
+int flip_to_pending_scene(bpt_ctx* ctx) {
+    if (!ctx->pending) return BPT_OK;
+    int target = 1 - ctx->active_set;
+    CK(cudaStreamWaitEvent(ctx->stream, ctx->sets[target].uploaded, 0));
+    DScene n = ctx->pending_sc;
+    n.strata_perm = ctx->sc.strata_perm; n.bn_sobol = ctx->sc.bn_sobol; n.bn_scramble = ctx->sc.bn_scramble; n.bn_rank = ctx->sc.bn_rank;
+    n.error_flag = ctx->sc.error_flag;
+    n.film_w = ctx->sc.film_w; n.film_h = ctx->sc.film_h;
+    ctx->sc = n;
+    ctx->active_set = target;
+    ctx->tri_original = ctx->sets[target].tri_original;
+    ctx->stack_bound = ctx->sets[target].stack_bound;
+    ctx->pending = false;
+    ctx->scene_ready = true;
+    return BPT_OK;
+}
+
+// a pass / trace over the active scene set has just been enqueued on ctx->stream
+void mark_scene_use(bpt_ctx* ctx) {
+    bpt_ctx::SceneSet& set = ctx->sets[ctx->active_set];
+    cudaEventRecord(set.last_use, ctx->stream);
+    set.used = true;
 }
 
 // what the kernels raised since the last check (the stream they ran on has been synchronised by the caller)
@@ -256,7 +299,15 @@ int bpt_create(int device, bpt_ctx** out_ctx) {
     }
     CK(cudaMalloc((void**)&ctx->d_stats, sizeof(DStats)));
     CK(cudaMemset(ctx->d_stats, 0, sizeof(DStats)));
-    CK(cudaMalloc((void**)&ctx->d_filter, 512*sizeof(float)));
+    CK(cudaStreamCreateWithFlags(&ctx->h2d_stream, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&ctx->d2h_stream, cudaStreamNonBlocking));
+    for (auto& set : ctx->sets) {
+        CK(cudaMalloc((void**)&set.d_filter, 512*sizeof(float)));
+        CK(cudaEventCreateWithFlags(&set.last_use, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&set.uploaded, cudaEventDisableTiming));
+    }
+    CK(cudaEventCreateWithFlags(&ctx->front_ready, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&ctx->download_done, cudaEventDisableTiming));
     CK(cudaHostAlloc((void**)&ctx->h_error, 64, cudaHostAllocMapped));
     *ctx->h_error = BPT_DEVERR_NONE;
     CK(cudaHostGetDevicePointer((void**)&ctx->sc.error_flag, ctx->h_error, 0));
@@ -288,9 +339,21 @@ void bpt_destroy(bpt_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    free_all(&ctx->scene_allocs);
-    for (auto& sl : ctx->slots) if (sl.p) cudaFree(sl.p);
-    if (ctx->staging) cudaFreeHost(ctx->staging);
+    if (ctx->h2d_stream) cudaStreamSynchronize(ctx->h2d_stream);
+    if (ctx->d2h_stream) cudaStreamSynchronize(ctx->d2h_stream);
+    for (auto& set : ctx->sets) {
+        for (auto& sl : set.slots) if (sl.p) cudaFree(sl.p);
+        if (set.staging) cudaFreeHost(set.staging);
+        cudaFree(set.d_filter);
+        if (set.last_use) cudaEventDestroy(set.last_use);
+        if (set.uploaded) cudaEventDestroy(set.uploaded);
+    }
+    for (auto& sl : ctx->misc_slots) if (sl.p) cudaFree(sl.p);
+    cudaFree(ctx->film_front);
+    if (ctx->front_ready) cudaEventDestroy(ctx->front_ready);
+    if (ctx->download_done) cudaEventDestroy(ctx->download_done);
+    if (ctx->h2d_stream) cudaStreamDestroy(ctx->h2d_stream);
+    if (ctx->d2h_stream) cudaStreamDestroy(ctx->d2h_stream);
     for (auto& pp : ctx->pipes) {
         cudaStreamSynchronize(pp.stream);
         free_all(&pp.allocs);
@@ -301,7 +364,7 @@ void bpt_destroy(bpt_ctx* ctx) {
     cudaFree(ctx->d_row_map);
     if (ctx->film_owned && ctx->film) cudaFree(ctx->film);
     cudaFree(ctx->film_reduced);
-    cudaFree(ctx->d_stats); cudaFree(ctx->d_filter);
+    cudaFree(ctx->d_stats);
     if (ctx->h_error) cudaFreeHost(ctx->h_error);
     cudaFree(ctx->d_perm); cudaFree(ctx->d_sobol); cudaFree(ctx->d_scramble); cudaFree(ctx->d_rank);
     for (auto& s : ctx->spans) { cudaEventDestroy(s.a); cudaEventDestroy(s.b); }
@@ -333,22 +396,29 @@ int bpt_set_sampler_tables(bpt_ctx* ctx, const uint8_t* perm, const uint8_t* sob
 int bpt_update_settings(bpt_ctx* ctx, const bpt_scene* scene) {
     if (!ctx || !scene) { set_error("bpt_update_settings: null argument"); return BPT_ERR_ARG; }
     CK(cudaSetDevice(ctx->device));
-    latch_settings(ctx, scene);
-    CK(cudaMemcpyAsync(ctx->d_filter, scene->filter.cache, 512*sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    { int rc = flip_to_pending_scene(ctx); if (rc) return rc; }
+    latch_settings(&ctx->sc, scene);
+    float* d_filter = ctx->sets[ctx->active_set].d_filter;
+    CK(cudaMemcpyAsync(d_filter, scene->filter.cache, 512*sizeof(float), cudaMemcpyHostToDevice, ctx->stream));   // behind the passes that still read the old LUT
     ctx->h2d_bytes += 512*sizeof(float) + sizeof(bpt_camera) + sizeof(bpt_settings);
     CK(cudaStreamSynchronize(ctx->stream));
-    ctx->sc.filter_lut = ctx->d_filter;
+    ctx->sc.filter_lut = d_filter;
     return BPT_OK;
 }
 
-int bpt_upload_scene(bpt_ctx* ctx, const bpt_scene* scene) {
+int bpt_upload_scene_async(bpt_ctx* ctx, const bpt_scene* scene) {
     if (!ctx || !scene) { set_error("bpt_upload_scene: null argument"); return BPT_ERR_ARG; }
     if (!scene->has_tlas) { set_error("bpt_upload_scene: call bpt_create_scene_bvh first"); return BPT_ERR_STATE; }
     CK(cudaSetDevice(ctx->device));
-    CK(cudaStreamSynchronize(ctx->stream));          // nothing may still be traversing the previous scene
-    ctx->scene_ready = false;
-    DScene& sc = ctx->sc;
-    cudaStream_t s = ctx->stream;
+    // The set that is NOT being rendered receives the upload, on the copy stream: passes over the active set keep running.
+    const int target = 1 - ctx->active_set;
+    bpt_ctx::SceneSet& set = ctx->sets[target];
+    cudaStream_t s = ctx->h2d_stream;
+    if (set.staged) CK(cudaEventSynchronize(set.uploaded));            // its pinned staging block is about to be rewritten by the host
+    if (set.used) CK(cudaStreamWaitEvent(s, set.last_use, 0));         // the last pass that read this set must be through
+    ctx->pending = false;                                              // an earlier upload nobody rendered is replaced
+    ctx->pending_sc = DScene{};
+    DScene& sc = ctx->pending_sc;
 
     if (scene->materials.size() + 1 > 0xFFFF) { set_error("bpt_upload_scene: more than 65534 materials"); return BPT_ERR_UNSUPPORTED; }
     for (uint32_t l : scene->lights) {
@@ -361,13 +431,13 @@ int bpt_upload_scene(bpt_ctx* ctx, const bpt_scene* scene) {
     size_t n_mats = scene->materials.size() + 1, n_prims = scene->primitives.size(), n_planes = scene->planes.size(),
            n_meshes = scene->meshes.size(), n_lights = scene->lights.size();
     size_t small_bytes = n_mats*sizeof(DMaterial) + n_prims*sizeof(DPrimitive) + n_planes*sizeof(DPlane) + n_meshes*sizeof(DMesh) + 1024;
-    if (ctx->staging_capacity < small_bytes) {
-        if (ctx->staging) cudaFreeHost(ctx->staging);
-        ctx->staging = nullptr; ctx->staging_capacity = 0;
-        CK(cudaHostAlloc((void**)&ctx->staging, small_bytes*2, cudaHostAllocDefault));
-        ctx->staging_capacity = small_bytes*2;
+    if (set.staging_capacity < small_bytes) {
+        if (set.staging) cudaFreeHost(set.staging);
+        set.staging = nullptr; set.staging_capacity = 0;
+        CK(cudaHostAlloc((void**)&set.staging, small_bytes*2, cudaHostAllocDefault));
+        set.staging_capacity = small_bytes*2;
     }
-    char* stage = ctx->staging;
+    char* stage = set.staging;
     auto carve = [&](size_t bytes) { char* p = stage; stage += (bytes + 255) & ~(size_t)255; return p; };
     DMaterial* mats = (DMaterial*)carve(n_mats*sizeof(DMaterial));
     DPrimitive* prims = (DPrimitive*)carve(n_prims*sizeof(DPrimitive));
@@ -422,12 +492,12 @@ int bpt_upload_scene(bpt_ctx* ctx, const bpt_scene* scene) {
         deepest_blas = std::max(deepest_blas, m.bvh.wide.depth);
     }
     if (total_pairs > 0x7FFFFFFFull || total_tris > 0x7FFFFFFFull) { set_error("bpt_upload_scene: scene too large for 32-bit pair / triangle indices"); return BPT_ERR_UNSUPPORTED; }
-    ctx->stack_bound = scene->tlas.wide.depth + deepest_blas;
+    set.stack_bound = scene->tlas.wide.depth + deepest_blas;
     sc.tame_bounds = tame ? 1u : 0u;
     memcpy(&sc.tlas_root_q0, &scene->tlas.wide.root, sizeof(WChild));
 
     void* d = nullptr;
-    #define SLOT(id, bytes) do { int rc_ = device_slot(ctx, id, (bytes), &d); if (rc_) return rc_; } while (0)
+    #define SLOT(id, bytes) do { int rc_ = device_slot(set.slots, id, (bytes), &d); if (rc_) return rc_; } while (0)
     #define H2D(dst, src, bytes) do { if ((bytes) > 0) { CK(cudaMemcpyAsync((dst), (src), (bytes), cudaMemcpyHostToDevice, s)); ctx->h2d_bytes += (bytes); } } while (0)
     SLOT(SL_MATERIALS, n_mats*sizeof(DMaterial));   sc.materials = (const DMaterial*)d;   H2D(d, mats, n_mats*sizeof(DMaterial));
     SLOT(SL_PRIMITIVES, n_prims*sizeof(DPrimitive)); sc.primitives = (const DPrimitive*)d; H2D(d, prims, n_prims*sizeof(DPrimitive));
@@ -441,7 +511,7 @@ int bpt_upload_scene(bpt_ctx* ctx, const bpt_scene* scene) {
     SLOT(SL_PAIRS, total_pairs*sizeof(DPair));             DPair* d_pairs = (DPair*)d;              sc.pairs = d_pairs;
     SLOT(SL_BIG_LEAVES, total_big*sizeof(uint2));          uint2* d_big = (uint2*)d;                sc.big_leaves = d_big;
     SLOT(SL_TRIANGLES, total_tris*sizeof(DTriangle));      DTriangle* d_tris = (DTriangle*)d;       sc.triangles = d_tris;
-    SLOT(SL_TRI_ORIGINAL, total_tris*sizeof(uint32_t));    uint32_t* d_orig = (uint32_t*)d;         ctx->tri_original = d_orig;
+    SLOT(SL_TRI_ORIGINAL, total_tris*sizeof(uint32_t));    uint32_t* d_orig = (uint32_t*)d;         set.tri_original = d_orig;
     SLOT(SL_RAW_TRIANGLES, total_tris*9*sizeof(float));    float* d_raw = (float*)d;
     float4* d_normals = nullptr; float* d_raw_normals = nullptr;
     sc.normals = nullptr;
@@ -484,12 +554,24 @@ int bpt_upload_scene(bpt_ctx* ctx, const bpt_scene* scene) {
     sc.air_material = sc.material_count;
     sc.light_count = (uint32_t)n_lights;
 
-    int rc = bpt_update_settings(ctx, scene);
-    if (rc) return rc;
-    CK(cudaStreamSynchronize(ctx->stream));
+    // camera / settings / filter latch with the upload (render_all_tiles :711-720)
+    latch_settings(&sc, scene);
+    CK(cudaMemcpyAsync(set.d_filter, scene->filter.cache, 512*sizeof(float), cudaMemcpyHostToDevice, s));
+    ctx->h2d_bytes += 512*sizeof(float) + sizeof(bpt_camera) + sizeof(bpt_settings);
+    sc.filter_lut = set.d_filter;
+    CK(cudaEventRecord(set.uploaded, s));
     CK(cudaGetLastError());
-    ctx->scene_ready = true;
+    set.staged = true;
+    ctx->pending = true;
     return BPT_OK;
+}
+
+int bpt_upload_scene(bpt_ctx* ctx, const bpt_scene* scene) {
+    int rc = bpt_upload_scene_async(ctx, scene);
+    if (rc) return rc;
+    CK(cudaStreamSynchronize(ctx->h2d_stream));      // the synchronous form: on return the scene is on the device and active
+    CK(cudaGetLastError());
+    return flip_to_pending_scene(ctx);
 }
 
 int bpt_film_resize(bpt_ctx* ctx, uint32_t w, uint32_t h) {
@@ -539,6 +621,52 @@ int bpt_download_film(bpt_ctx* ctx, float* out) {
     return device_error(ctx, "bpt_download_film");
 }
 
+// Snapshot + asynchronous read-back.  The film is copied device-to-device into a front buffer behind everything enqueued so
+// far (the reference's "copy back buffer to front buffer", raytracer.cpp:705-709), and the front buffer goes to the host on
+// a copy stream: the next pass can clear / accumulate into the film while the previous image is still on its way out.
+int bpt_download_film_async(bpt_ctx* ctx, float* out, int reduced) {
+    if (!ctx || !out) { set_error("bpt_download_film_async: null argument"); return BPT_ERR_ARG; }
+    const float4* src = reduced ? ctx->film_reduced : ctx->film;
+    if (!src) { set_error("bpt_download_film_async: no %sfilm", reduced ? "reduced " : ""); return BPT_ERR_STATE; }
+    CK(cudaSetDevice(ctx->device));
+    size_t bytes = (size_t)ctx->film_w*ctx->film_h*sizeof(float4);
+    if (!ctx->film_front || ctx->film_front_w != ctx->film_w || ctx->film_front_h != ctx->film_h) {
+        CK(cudaStreamSynchronize(ctx->d2h_stream));
+        cudaFree(ctx->film_front); ctx->film_front = nullptr;
+        CK(cudaMalloc((void**)&ctx->film_front, bytes));
+        ctx->film_front_w = ctx->film_w; ctx->film_front_h = ctx->film_h;
+        ctx->download_pending = false;
+    }
+    if (ctx->download_pending) CK(cudaStreamWaitEvent(ctx->stream, ctx->download_done, 0));   // the previous read-back still reads the front buffer
+    CK(cudaMemcpyAsync(ctx->film_front, src, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+    CK(cudaEventRecord(ctx->front_ready, ctx->stream));
+    CK(cudaStreamWaitEvent(ctx->d2h_stream, ctx->front_ready, 0));
+    CK(cudaMemcpyAsync(out, ctx->film_front, bytes, cudaMemcpyDeviceToHost, ctx->d2h_stream));    // `out` should be page-locked (bpt_host_register)
+    CK(cudaEventRecord(ctx->download_done, ctx->d2h_stream));
+    ctx->download_pending = true;
+    ctx->d2h_bytes += bytes;
+    return BPT_OK;
+}
+
+int bpt_wait_download(bpt_ctx* ctx) {
+    if (!ctx) { set_error("bpt_wait_download: null ctx"); return BPT_ERR_ARG; }
+    CK(cudaSetDevice(ctx->device));
+    if (ctx->download_pending) CK(cudaEventSynchronize(ctx->download_done));
+    return device_error(ctx, "bpt_wait_download");
+}
+
+int bpt_host_register(void* host_ptr, size_t bytes) {
+    if (!host_ptr || bytes == 0) { set_error("bpt_host_register: bad arguments"); return BPT_ERR_ARG; }
+    CK(cudaHostRegister(host_ptr, bytes, cudaHostRegisterDefault));
+    return BPT_OK;
+}
+
+int bpt_host_unregister(void* host_ptr) {
+    if (!host_ptr) return BPT_OK;
+    CK(cudaHostUnregister(host_ptr));
+    return BPT_OK;
+}
+
 int bpt_sync(bpt_ctx* ctx) {
     if (!ctx) { set_error("bpt_sync: null ctx"); return BPT_ERR_ARG; }
     CK(cudaSetDevice(ctx->device));
@@ -579,15 +707,16 @@ int bpt_set_sample_records(bpt_ctx* ctx, bpt_sample_record* host_records, uint64
 
 int bpt_trace(bpt_ctx* ctx, uint32_t n, const bpt_ray* rays, int mode, uint32_t ignored, bpt_hit* out) {
     if (!ctx || (n && (!rays || !out))) { set_error("bpt_trace: null argument"); return BPT_ERR_ARG; }
+    { int rc_ = flip_to_pending_scene(ctx); if (rc_) return rc_; }
     if (!ctx->scene_ready) { set_error("bpt_trace: no scene uploaded"); return BPT_ERR_STATE; }
     if (mode != BPT_TRACE_CLOSEST && mode != BPT_TRACE_OCCLUSION) { set_error("bpt_trace: bad mode"); return BPT_ERR_ARG; }
     if (n == 0) return BPT_OK;
     CK(cudaSetDevice(ctx->device));
     // grow-only device buffers owned by the context (no allocation per call, nothing to leak on an error path)
     void* d = nullptr;
-    int rc = device_slot(ctx, SL_TRACE_RAYS, (size_t)n*sizeof(bpt_ray), &d);   if (rc) return rc;  bpt_ray* d_rays = (bpt_ray*)d;
-    rc = device_slot(ctx, SL_TRACE_HITS, (size_t)n*sizeof(bpt_hit), &d);       if (rc) return rc;  bpt_hit* d_hits = (bpt_hit*)d;
-    rc = device_slot(ctx, SL_TRACE_CURSOR, 256, &d);                           if (rc) return rc;  uint32_t* d_cursor = (uint32_t*)d;
+    int rc = device_slot(ctx->misc_slots, SL_TRACE_RAYS, (size_t)n*sizeof(bpt_ray), &d);   if (rc) return rc;  bpt_ray* d_rays = (bpt_ray*)d;
+    rc = device_slot(ctx->misc_slots, SL_TRACE_HITS, (size_t)n*sizeof(bpt_hit), &d);       if (rc) return rc;  bpt_hit* d_hits = (bpt_hit*)d;
+    rc = device_slot(ctx->misc_slots, SL_TRACE_CURSOR, 256, &d);                           if (rc) return rc;  uint32_t* d_cursor = (uint32_t*)d;
     CK(cudaMemcpyAsync(d_rays, rays, (size_t)n*sizeof(bpt_ray), cudaMemcpyHostToDevice, ctx->stream));
     ctx->h2d_bytes += (uint64_t)n*sizeof(bpt_ray); ctx->d2h_bytes += (uint64_t)n*sizeof(bpt_hit);
     CK(cudaMemsetAsync(d_cursor, 0, 256, ctx->stream));
@@ -601,6 +730,7 @@ int bpt_trace(bpt_ctx* ctx, uint32_t n, const bpt_ray* rays, int mode, uint32_t 
         else    k_trace_api<true, false><<<grid, BPT_TRACE_THREADS, 0, ctx->stream>>>(ctx->sc, d_rays, n, ignored, d_hits, ctx->tri_original, d_cursor, ctx->refill, ctx->d_stats);
     }
     ctx->total_launches += 1;
+    mark_scene_use(ctx);
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(out, d_hits, (size_t)n*sizeof(bpt_hit), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
@@ -609,6 +739,7 @@ int bpt_trace(bpt_ctx* ctx, uint32_t n, const bpt_ray* rays, int mode, uint32_t 
 
 static int render_rows(bpt_ctx* ctx, int32_t x0, int32_t x1, const std::vector<int32_t>& rows,
                        uint32_t frame_count, uint32_t spp, uint32_t seed_mode, uint32_t seed_salt, const char* who) {
+    { int rc_ = flip_to_pending_scene(ctx); if (rc_) return rc_; }     // a scene uploaded asynchronously becomes the active one here
     if (!ctx->scene_ready) { set_error("%s: no scene uploaded", who); return BPT_ERR_STATE; }
     if (!ctx->tables_ready) { set_error("%s: sampler tables not set (bpt_set_sampler_tables)", who); return BPT_ERR_STATE; }
     if (!ctx->film) { set_error("%s: no film (bpt_film_resize)", who); return BPT_ERR_STATE; }
@@ -820,6 +951,7 @@ retry_shape:
         CK(cudaStreamWaitEvent(ctx->stream, ctx->pipes[p].done, 0));
     }
     CK(cudaEventRecord(ctx->pass_end, ctx->stream));
+    mark_scene_use(ctx);
     ctx->pass_recorded = true;
     ctx->total_launches += ctx->launches;
     ctx->samples += total_samples;
@@ -831,7 +963,7 @@ int bpt_render_pass(bpt_ctx* ctx, int32_t x0, int32_t y0, int32_t x1, int32_t y1
                     uint32_t frame_count, uint32_t spp, uint32_t seed_mode, uint32_t seed_salt) {
     if (!ctx) { set_error("bpt_render_pass: null ctx"); return BPT_ERR_ARG; }
     if (y0 < 0 || y0 >= y1 || y1 > (int32_t)ctx->film_h) {
-        if (!ctx->scene_ready) { set_error("bpt_render_pass: no scene uploaded"); return BPT_ERR_STATE; }
+        if (!ctx->scene_ready && !ctx->pending) { set_error("bpt_render_pass: no scene uploaded"); return BPT_ERR_STATE; }
         if (!ctx->film) { set_error("bpt_render_pass: no film (bpt_film_resize)"); return BPT_ERR_STATE; }
         set_error("bpt_render_pass: bad rect/spp"); return BPT_ERR_ARG;
     }
@@ -881,11 +1013,11 @@ static int resolve_film(bpt_ctx* ctx, const float4* film, const bpt_post_setting
     CK(cudaSetDevice(ctx->device));
     size_t n = (size_t)ctx->film_w*ctx->film_h;
     void* d = nullptr;
-    int rc = device_slot(ctx, SL_RESOLVE_OUT, n*sizeof(uint32_t), &d);   if (rc) return rc;   uint32_t* d_out = (uint32_t*)d;
+    int rc = device_slot(ctx->misc_slots, SL_RESOLVE_OUT, n*sizeof(uint32_t), &d);   if (rc) return rc;   uint32_t* d_out = (uint32_t*)d;
     uint8_t* d_dither = nullptr;
     if (dither_rgb8) {
         size_t db = (size_t)dither_w*dither_h*3;
-        rc = device_slot(ctx, SL_RESOLVE_DITHER, db, &d);   if (rc) return rc;   d_dither = (uint8_t*)d;
+        rc = device_slot(ctx->misc_slots, SL_RESOLVE_DITHER, db, &d);   if (rc) return rc;   d_dither = (uint8_t*)d;
         CK(cudaMemcpyAsync(d_dither, dither_rgb8, db, cudaMemcpyHostToDevice, ctx->stream));
         ctx->h2d_bytes += db;
     }

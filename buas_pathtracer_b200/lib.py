@@ -106,6 +106,17 @@ def load_library():
     L.bpt_resolve_bgra8.argtypes = [vp, P(capi.PostSettings), vp, C.c_uint32, C.c_uint32, vp]
     L.bpt_write_bitmap.restype = C.c_int
     L.bpt_write_bitmap.argtypes = [C.c_char_p, vp, C.c_uint32, C.c_uint32]
+    if hasattr(L, "bpt_upload_scene_async"):
+        L.bpt_upload_scene_async.restype = C.c_int
+        L.bpt_upload_scene_async.argtypes = [vp, vp]
+        L.bpt_download_film_async.restype = C.c_int
+        L.bpt_download_film_async.argtypes = [vp, vp, C.c_int]
+        L.bpt_wait_download.restype = C.c_int
+        L.bpt_wait_download.argtypes = [vp]
+        L.bpt_host_register.restype = C.c_int
+        L.bpt_host_register.argtypes = [vp, C.c_size_t]
+        L.bpt_host_unregister.restype = C.c_int
+        L.bpt_host_unregister.argtypes = [vp]
     if hasattr(L, "bpt_reduce_film"):
         L.bpt_nccl_get_unique_id.restype = C.c_int
         L.bpt_nccl_get_unique_id.argtypes = [vp]
@@ -275,6 +286,23 @@ class Renderer:
 
     def upload_scene(self, scene):
         _check(self.lib.bpt_upload_scene(self.handle, scene.handle), "bpt_upload_scene")
+
+    def upload_scene_async(self, scene):
+        """bpt_upload_scene_async: into the inactive scene buffer on a copy stream; the next pass switches to it"""
+        _check(self.lib.bpt_upload_scene_async(self.handle, scene.handle), "bpt_upload_scene_async")
+
+    def download_film_async(self, out, reduced=False):
+        """snapshot the film behind the passes enqueued so far and start its copy to `out` (page-locked, see host_register)"""
+        _check(self.lib.bpt_download_film_async(self.handle, out.ctypes.data, int(reduced)), "bpt_download_film_async")
+
+    def wait_download(self):
+        _check(self.lib.bpt_wait_download(self.handle), "bpt_wait_download")
+
+    def host_register(self, array):
+        _check(self.lib.bpt_host_register(array.ctypes.data, array.nbytes), "bpt_host_register")
+
+    def host_unregister(self, array):
+        _check(self.lib.bpt_host_unregister(array.ctypes.data), "bpt_host_unregister")
 
     def update_settings(self, scene):
         _check(self.lib.bpt_update_settings(self.handle, scene.handle), "bpt_update_settings")

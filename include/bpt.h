@@ -303,6 +303,11 @@ BPT_API int bpt_set_sampler_tables(bpt_ctx* ctx, const uint8_t* strata_permutati
  * TLAS, one BLAS per unique mesh (child-pair nodes, 48-B triangles), skydome, camera, settings,
  * filter LUT.  Replaces handing `Scene*` to the worker threads (Raytracer.h:50-55). */
 BPT_API int bpt_upload_scene(bpt_ctx* ctx, const bpt_scene* scene);
+/* The same without waiting: the upload runs on a copy stream into the scene buffer that is NOT being rendered (the device
+ * holds two), so passes enqueued earlier keep running over the previous scene; the next bpt_render_pass / bpt_trace
+ * switches to the new one (ordered on the device, no host wait).  `scene` must stay unmodified until then.  This is how a
+ * host loop that re-submits its scene every frame overlaps the transfer with rendering (bench.py's e2e leg). */
+BPT_API int bpt_upload_scene_async(bpt_ctx* ctx, const bpt_scene* scene);
 /* Re-latch camera/settings/filter only (render_all_tiles :700-720) without touching geometry. */
 BPT_API int bpt_update_settings(bpt_ctx* ctx, const bpt_scene* scene);
 
@@ -312,6 +317,14 @@ BPT_API int bpt_film_clear(bpt_ctx* ctx);
 BPT_API int bpt_film_use_external(bpt_ctx* ctx, void* device_ptr, uint32_t w, uint32_t h); /* caller-owned device buffer (e.g. a torch tensor for the NCCL reduce) */
 BPT_API int bpt_film_device_ptr(bpt_ctx* ctx, void** out_device_ptr);
 BPT_API int bpt_download_film(bpt_ctx* ctx, float* out_rgba /* w*h*4 floats, host */);
+/* Snapshot + asynchronous read-back: the film (reduced != 0: the root's reduced film) is copied into a front buffer behind
+ * the passes enqueued so far -- what render_all_tiles does when a pass completes (copy to the front buffer, raytracer.cpp:
+ * 705-709) -- and that snapshot travels to `out_rgba` on a copy stream while later passes already run.  `out_rgba` should
+ * be page-locked (bpt_host_register) for the copy to be asynchronous; it is valid after bpt_wait_download. */
+BPT_API int bpt_download_film_async(bpt_ctx* ctx, float* out_rgba, int reduced);
+BPT_API int bpt_wait_download(bpt_ctx* ctx);
+BPT_API int bpt_host_register(void* host_ptr, size_t bytes);       /* cudaHostRegister / cudaHostUnregister */
+BPT_API int bpt_host_unregister(void* host_ptr);
 
 /* One progressive pass over the pixel rect [x0,x1) x [y0,y1): what render_all_tiles + every
  * render_tile call of the pass do (raytracer.cpp:366-495, :692-757).  `frame_count` is
