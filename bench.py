@@ -350,7 +350,7 @@ def main():
         if rank == 0:
             for hf in host_films:
                 r.host_register(hf)
-        n_e2e = max(2, min(args.steps, 5))
+        n_e2e = max(3, args.steps)
         r.sync()
         r.transfer_bytes(reset=True)
         if dist is not None:

@@ -909,7 +909,7 @@ retry_shape:
                     ctx->launches++; ctx->trace_launches++;
                 }
                 begin_span(ctx, ST_SHADE, s);
-                k_shade<<<grid_for(ctx, work, BPT_SHADE_THREADS, 4), BPT_SHADE_THREADS, 0, s>>>(sc, pp.st, b, bounce, in_queue, in_count, b.slots,
+                k_shade<<<grid_for(ctx, work, BPT_SHADE_THREADS, BPT_SHADE_MIN_CTAS), BPT_SHADE_THREADS, 0, s>>>(sc, pp.st, b, bounce, in_queue, in_count, b.slots,
                                                                     pp.q.active[out], counters + out, pp.q.shadow, counters + 2, ctx->d_stats);
                 debug_sync("k_shade", bounce, s);
                 end_span(ctx, s);

@@ -17,8 +17,12 @@ REFERENCE_ROOT = "/root/reference"
 def build(force=False):
     """(Re)build the oracle when the reference tree is present; on the GPU box the prebuilt .so is used."""
     if os.path.isdir(os.path.join(REFERENCE_ROOT, "Raytracer")):
-        args = ["make", "-C", HERE, "-j8"] + (["-B"] if force else [])
+        args = ["make", "-C", HERE, "-j8", "all"] + (["-B"] if force else [])
         subprocess.run(args, check=True, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
+        # INTEGRATION.md's binding compiled against the reference's Scene and linked with the product library (test-only);
+        # needs libbpt.so, so it is best-effort here
+        if os.path.exists(os.path.join(HERE, "..", "buas_pathtracer_b200", "libbpt.so")):
+            subprocess.run(["make", "-C", HERE, "integration"], stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
     return os.path.exists(LIB_PATH)
 
 

@@ -390,6 +390,51 @@ BPT_API int ref_write_bitmap(const char* file_name, const uint32_t* pixels, uint
 
 } // extern "C"
 
+#ifdef ORACLE_WITH_INTEGRATION
+// ---- INTEGRATION.md's binding, compiled as written against the reference's own Scene (oracle/_ref/libbpt_integration.so
+//      only: the one artefact in which reference code and the product library meet; nothing else loads it) ----------------
+#include "integration/raytracer_bpt.inl"
+
+extern "C" int ref_get_sampler_tables(uint8_t* perm, uint8_t* sobol, uint8_t* scramble, uint8_t* rank);   // tu_samplers.cpp
+
+// load_scene(g_scenes[name]) exactly like SDL_main (raytracer.cpp:1455-1470, :1630) -> bpt_mirror_scene -> `passes` calls
+// of render_all_tiles_bpt -> the front buffer.  `scene_out` (nullable) receives the ref_scene so the caller can render the
+// very same Scene with the reference's own CPU path.
+extern "C" BPT_API int integration_render_builtin(ref_scene* s, const char* name, uint32_t w, uint32_t h, uint32_t spp,
+                                                  uint32_t passes, int device, float* film_out) {
+    if (ref_load_builtin_scene(s, name, w, h) != 0) return -1;
+    Scene* scene = &s->scene;
+    scene->new_settings.samples_per_pixel = spp;
+    static uint8_t perm[16384], sobol[65536], scr[131072], rank[131072];
+    if (ref_get_sampler_tables(perm, sobol, scr, rank) != 0) return -2;
+
+    BptBridge bridge = {};
+    if (bpt_create(device, &bridge.ctx) != BPT_OK) { fprintf(stderr, "bpt: %s\n", bpt_last_error()); return -3; }
+    int rc = 0;
+    AccumulationBuffer back = {}, front = {};
+    std::vector<V4> back_px((size_t)w*h), front_px((size_t)w*h);
+    back.w = front.w = w; back.h = front.h = h; back.pixels = back_px.data(); front.pixels = front_px.data();
+    RenderParameters params = {};
+    params.scene = scene; params.backbuffer = &back; params.frontbuffer = &front;
+    if (bpt_set_sampler_tables(bridge.ctx, perm, sobol, scr, rank) != BPT_OK) rc = -4;
+    if (!rc) {
+        bpt_mirror_scene(&bridge, scene);
+        scene->camera = scene->new_camera; scene->settings = scene->new_settings;      // the first latch of render_all_tiles (:711-720)
+        recompute_camera(&scene->camera);
+        bpt_latch(&bridge, scene);
+        if (bpt_upload_scene(bridge.ctx, bridge.mirror) != BPT_OK || bpt_film_resize(bridge.ctx, w, h) != BPT_OK) rc = -5;
+    }
+    for (uint32_t p = 0; !rc && p < passes; ++p)
+        if (!render_all_tiles_bpt(&bridge, &params)) rc = -6;
+    if (!rc) memcpy(film_out, front.pixels, sizeof(V4)*(size_t)w*h);
+    if (rc) fprintf(stderr, "integration: rc %d: %s\n", rc, bpt_last_error());
+    if (bridge.mirror) bpt_scene_destroy(bridge.mirror);
+    bpt_destroy(bridge.ctx);
+    s->latched = false;
+    return rc;
+}
+#endif
+
 // ---- the reference's asset parsers (assets.cpp, compiled unmodified into assets.o) ---------------------------------
 #include <sys/mman.h>
 static void release_arena(Arena* a) { if (a->base) munmap(a->base, a->capacity); delete a; }
