@@ -256,10 +256,21 @@ k_raygen(DScene sc, DPathState st, BatchDesc b) {
 
         V2 aa = sample_2d(sm, rng, Sample_AA, 0);
         float jx = aa.x - 0.5f, jy = aa.y - 0.5f;
-        V2 dof = sample_2d(sm, rng, Sample_DOF, 0);
-        dof = transform_bokeh_sample(dof, sc.settings.f_factor, sc.settings.diaphragm_edges, kPi*sc.settings.phi_shutter_max);
-        float dof_x = half_w*pixel_w*lens_radius*dof.x;
-        float dof_y = half_h*pixel_h*lens_radius*dof.y;
+        // With lens_radius == 0 the lens sample is multiplied by zero: dof_x / dof_y are +-0 and
+        // cam_p + (+-0)*cam_x + (+-0)*cam_y is cam_p bit for bit -- unless a component of cam_p is -0.0 (the sum's zero would
+        // take its sign from the sample) or the camera basis is not finite.  In that (usual) case the DOF draw and the
+        // polygonal-bokeh transform (cos / sin / pow in double) are skipped; the RNG state the first shade re-derives
+        // (primary_rng_state) does not depend on them being executed here.
+        const bool lens_inert = lens_radius == 0.0f &&
+                                __float_as_uint(cam_p.x) != 0x80000000u && __float_as_uint(cam_p.y) != 0x80000000u && __float_as_uint(cam_p.z) != 0x80000000u &&
+                                fabsf(cam_x.x) + fabsf(cam_x.y) + fabsf(cam_x.z) + fabsf(cam_y.x) + fabsf(cam_y.y) + fabsf(cam_y.z) + fabsf(half_w*pixel_w) + fabsf(half_h*pixel_h) < 3.0e38f;
+        float dof_x = 0.0f, dof_y = 0.0f;
+        if (!lens_inert) {
+            V2 dof = sample_2d(sm, rng, Sample_DOF, 0);
+            dof = transform_bokeh_sample(dof, sc.settings.f_factor, sc.settings.diaphragm_edges, kPi*sc.settings.phi_shutter_max);
+            dof_x = half_w*pixel_w*lens_radius*dof.x;
+            dof_y = half_h*pixel_h*lens_radius*dof.y;
+        }
 
         V3 film_p = film_center;
         film_p = film_p + (u + pixel_w*jx)*half_w*cam_x;

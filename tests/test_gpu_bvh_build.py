@@ -1,6 +1,7 @@
-"""GPU BVH construction: bpt_build_mesh_bvh_device must reproduce the host builder's output --
-which tests/test_host_parity.py pins memcmp-equal to the reference's create_bvh_for_mesh -- node for node:
-same node array (depth-first numbering, bounds, split axes, leaf ranges) and same leaf-order index array."""
+"""GPU BVH construction: bpt_build_mesh_bvh_device must reproduce, node for node, the output of the
+reference's own create_bvh_for_mesh (compared directly through the oracle) and of the host builder (which
+tests/test_host_parity.py pins memcmp-equal to the reference too): same node array (depth-first numbering, bounds, split
+axes, leaf ranges) and same leaf-order index array."""
 import numpy as np
 import pytest
 
@@ -8,6 +9,14 @@ import buas_pathtracer_b200 as B
 from buas_pathtracer_b200 import capi, lib, scenes
 
 pytestmark = pytest.mark.gpu
+
+
+def reference_build(oracle, tris, method=None):
+    """the reference's own create_bvh_for_mesh (bvh.cpp:342-426) through the oracle"""
+    s = oracle.RefScene()
+    m = s.create_mesh(tris, method=method)
+    nodes, idx, _ = s.mesh_bvh(m)
+    return nodes, idx
 
 
 def host_build(tris, method=None):
@@ -27,21 +36,26 @@ def assert_same_bvh(dn, di, hn, hi, what):
 
 
 @pytest.mark.parametrize("level", [0, 1, 3, 5, 7])
-def test_device_bvh_equals_host_bvh_icosphere(renderer, level):
+def test_device_bvh_equals_host_bvh_icosphere(renderer, oracle, level):
     tris = lib.make_displaced_icosphere(level)
     dn, di, ms = renderer.build_mesh_bvh(tris)
     hn, hi = host_build(tris)
     assert_same_bvh(dn, di, hn, hi, f"icosphere level {level}")
+    rn, ri = reference_build(oracle, tris)               # and directly against the reference's builder
+    assert_same_bvh(dn, di, rn, ri, f"icosphere level {level} vs the reference")
     print(f"icosphere level {level}: {tris.shape[0]} triangles, {dn.shape[0]} nodes, device build {ms:.2f} ms")
 
 
 @pytest.mark.parametrize("level", [0, 2, 4, 6, 8])
-def test_device_midpoint_bvh_equals_host(renderer, level):
+def test_device_midpoint_bvh_equals_host(renderer, oracle, level):
     """BVH_MidpointSplit (what the reference builds for OBJ files, raytracer.cpp:154) on the device"""
     tris = lib.make_displaced_icosphere(level)
     dn, di, ms = renderer.build_mesh_bvh(tris, capi.BVH_MIDPOINT_SPLIT)
     hn, hi = host_build(tris, capi.BVH_MIDPOINT_SPLIT)
     assert_same_bvh(dn, di, hn, hi, f"midpoint, icosphere level {level}")
+    if level <= 6:
+        rn, ri = reference_build(oracle, tris, capi.BVH_MIDPOINT_SPLIT)
+        assert_same_bvh(dn, di, rn, ri, f"midpoint, icosphere level {level} vs the reference")
     rng = np.random.RandomState(level)
     soup = np.ascontiguousarray((rng.rand(3000, 9) ** 5) * 40, np.float32)         # skewed: lopsided midpoints, forced leaves
     dn, di, _ = renderer.build_mesh_bvh(soup, capi.BVH_MIDPOINT_SPLIT)
@@ -50,7 +64,7 @@ def test_device_midpoint_bvh_equals_host(renderer, level):
     print(f"midpoint level {level}: {tris.shape[0]} triangles, device build {ms:.2f} ms")
 
 
-def test_device_bvh_degenerate_inputs(renderer):
+def test_device_bvh_degenerate_inputs(renderer, oracle):
     rng = np.random.RandomState(3)
     cases = {
         "one triangle": rng.rand(1, 9),
@@ -69,6 +83,8 @@ def test_device_bvh_degenerate_inputs(renderer):
         dn, di, _ = renderer.build_mesh_bvh(t)
         hn, hi = host_build(t)
         assert_same_bvh(dn, di, hn, hi, what)
+        rn, ri = reference_build(oracle, t)
+        assert_same_bvh(dn, di, rn, ri, what + " vs the reference")
 
 
 def test_device_bvh_signed_zero_ties_are_the_documented_limit(renderer):
@@ -106,8 +122,9 @@ def test_render_through_device_built_bvh(renderer):
     assert np.allclose(films[0], films[1], rtol=1e-5, atol=1e-6)
 
 
-def test_device_bvh_full_size_c2_mesh(renderer):
-    """BASELINE config 2's mesh: 1,310,720 triangles, bit-identical to the host build, and how long each takes"""
+def test_device_bvh_full_size_c2_mesh(renderer, oracle):
+    """BASELINE config 2's mesh: 1,310,720 triangles, bit-identical to the host build and to the reference's own
+    create_bvh_for_mesh, and how long each takes"""
     import time
     tris = lib.make_displaced_icosphere(8)
     renderer.build_mesh_bvh(tris[:1000])                  # warm-up (context, allocator)
@@ -116,5 +133,9 @@ def test_device_bvh_full_size_c2_mesh(renderer):
     hn, hi = host_build(tris)
     host_ms = (time.perf_counter() - t0) * 1e3
     assert_same_bvh(dn, di, hn, hi, "icosphere level 8")
+    t0 = time.perf_counter()
+    rn, ri = reference_build(oracle, tris)
+    ref_ms = (time.perf_counter() - t0) * 1e3
+    assert_same_bvh(dn, di, rn, ri, "icosphere level 8 vs the reference")
     print(f"icosphere level 8: {tris.shape[0]} triangles, {dn.shape[0]} nodes: device build {ms:.2f} ms, "
-          f"host build (incl. scene bookkeeping) {host_ms:.0f} ms")
+          f"host build (incl. scene bookkeeping) {host_ms:.0f} ms, the reference's create_bvh_for_mesh {ref_ms:.0f} ms")
