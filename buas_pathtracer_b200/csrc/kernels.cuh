@@ -744,6 +744,9 @@ BPT_D void shade_path(const DScene& sc, const DPathState& st, const BatchDesc& b
 #ifndef BPT_SHADE_SORT
 #define BPT_SHADE_SORT 1
 #endif
+#ifndef BPT_SHADE_SORT_BOUNCES
+#define BPT_SHADE_SORT_BOUNCES 64     // bounces < this group their survivors by octant with the block-local sort; later ones append per warp
+#endif
 #ifndef BPT_SHADE_SORT_MATERIAL
 #define BPT_SHADE_SORT_MATERIAL 0     // measured on B200: shade time C2 +0.8 %, C3 -2.5 %, C4 +4 % -> off (the kernel is bound by
 #endif                                // path-state traffic, not by branch divergence; parity tests pass with it on)
@@ -763,8 +766,11 @@ k_shade(DScene sc, DPathState st, BatchDesc b, uint32_t bounce,
         bool want_shadow = false;
         uint32_t slot = 0, octant = 0;
         DShadowItem sh;
-        if (threadIdx.x < 8) s_count[threadIdx.x] = 0;
-        __syncthreads();
+        const bool block_sort = BPT_SHADE_SORT != 0 && bounce < (uint32_t)BPT_SHADE_SORT_BOUNCES;      // uniform over the grid
+        if (block_sort) {
+            if (threadIdx.x < 8) s_count[threadIdx.x] = 0;
+            __syncthreads();
+        }
 
         bool have = i < n;
         if (have) slot = in_queue ? in_queue[i] : i;
@@ -800,30 +806,34 @@ k_shade(DScene sc, DPathState st, BatchDesc b, uint32_t bounce,
         }
 #endif
         if (have) shade_path(sc, st, b, bounce, slot, alive, want_shadow, sh, octant);
-#if !BPT_SHADE_SORT
-        octant = 0;
-#endif
-        // block-local counting sort of the survivors by octant (rank within the octant from a shared-memory atomic)
-        uint32_t rank = 0;
-        if (alive) rank = atomicAdd(&s_count[octant], 1u);
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            uint32_t run = 0;
-            for (int k = 0; k < 8; ++k) { s_start[k] = run; run += s_count[k]; }
-            s_base = run ? atomicAdd(out_count, run) : 0u;
-            s_count[0] = run;                                    // total survivors of this round
+        if (block_sort) {
+            // block-local counting sort of the survivors by octant (rank within the octant from a shared-memory atomic)
+            uint32_t rank = 0;
+            if (alive) rank = atomicAdd(&s_count[octant], 1u);
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                uint32_t run = 0;
+                for (int k = 0; k < 8; ++k) { s_start[k] = run; run += s_count[k]; }
+                s_base = run ? atomicAdd(out_count, run) : 0u;
+                s_count[0] = run;                                    // total survivors of this round
+            }
+            __syncthreads();
+            if (alive) s_slots[s_start[octant] + rank] = slot;
+            __syncthreads();
+            uint32_t total = s_count[0];
+            if (threadIdx.x < total) out_queue[s_base + threadIdx.x] = s_slots[threadIdx.x];
+        } else {
+            // no grouping: warp-aggregated append, no block barrier (the lanes of a late bounce take very different paths
+            // through shade_path; ncu showed warps of a block waiting 7-10 issue slots per instruction at the sort's barriers)
+            uint32_t qi = queue_append(out_count, alive);
+            if (alive) out_queue[qi] = slot;
         }
-        __syncthreads();
-        if (alive) s_slots[s_start[octant] + rank] = slot;
-        __syncthreads();
-        uint32_t total = s_count[0];
-        if (threadIdx.x < total) out_queue[s_base + threadIdx.x] = s_slots[threadIdx.x];
 
         uint32_t si = queue_append(shadow_count, want_shadow);
         if (want_shadow) shadow_items[si] = sh;
         n_rays += (have ? 1u : 0u) + (want_shadow ? 1u : 0u);
         n_shadow += want_shadow ? 1u : 0u;
-        __syncthreads();
+        if (block_sort) __syncthreads();
     }
     flush_ray_counts(stats, n_rays, n_shadow);
 }
