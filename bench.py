@@ -391,6 +391,44 @@ def main():
                        "bpt_download_film_async to a page-locked host array; copies of neighbouring steps overlap the rendering "
                        "(two scene buffers, front-buffer snapshot); wall clock over the loop incl. the wait for the last film"}
 
+    # --- extra key at 8 GPUs: BASELINE config 5 (3840x2160, 1024 spp, the instanced scene), 2 timed passes -----------
+    c5 = None
+    if world >= 8 and args.config == "c2" and os.environ.get("BPT_BENCH_C5", "1") != "0":
+        c5cfg = scenes.CONFIGS["c5"]
+        w5, h5, spp5 = c5cfg["w"], c5cfg["h"], c5cfg["spp"]
+        scene5 = B.Scene()
+        c5cfg["build"](scene5, w5, h5)
+        r.upload_scene(scene5)
+        r.film_resize(w5, h5)
+        bands5 = my_rows(h5, rank, world)
+
+        def step5():
+            r.render_pass_bands(spp5, bands5, frame_count=0)
+            r.reduce_film(comm, 0)
+            r.sync()
+
+        step5()                                            # warm-up (path-state allocation for the larger batches)
+        r.get_stats(reset=True)
+        dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        n5 = 2
+        for _ in range(n5):
+            step5()
+        e1.record()
+        torch.cuda.synchronize()
+        dist.barrier()
+        st5 = r.get_stats(reset=True)
+        v = torch.tensor([e0.elapsed_time(e1), float(st5.rays) / n5, float(sum(y1 - y0 for y0, y1 in bands5)) * w5 * spp5],
+                         dtype=torch.float64, device=f"cuda:{local_rank}")
+        mx = v.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        sm = v.clone(); dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+        ms5 = float(mx[0]) / n5
+        c5 = {"workload": c5cfg["name"], "n_gpus": world, "steps": n5, "ms_per_step": ms5,
+              "value": float(sm[1]) / (ms5 * 1e-3) / 1e6, "unit": "Mrays/s",
+              "samples_per_s": float(sm[2]) / (ms5 * 1e-3), "includes": "one NCCL reduce of the 132.7 MB film per pass"}
+
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -467,6 +505,8 @@ def main():
             "cpu_baseline": cpu_baseline}
     if multi_gpu_check is not None:
         line["multi_gpu_check"] = multi_gpu_check
+    if c5 is not None:
+        line["c5_at_8_gpus"] = c5
     print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()

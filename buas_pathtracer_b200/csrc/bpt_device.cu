@@ -82,7 +82,8 @@ struct bpt_ctx {
     struct Pipe {
         cudaStream_t stream = nullptr;
         cudaEvent_t done = nullptr;
-        uint32_t max_slots = 0;
+        uint32_t max_slots = 0, mstack_levels = 0;
+        bool has_record_arrays = false;
         DPathState st{};
         DQueues q{};
         std::vector<void*> allocs;
@@ -148,11 +149,16 @@ void free_all(std::vector<void*>* v) {
     v->clear();
 }
 
-int ensure_state(bpt_ctx* ctx, bpt_ctx::Pipe* pp, uint32_t slots) {
+// `levels`: material-stack levels beyond the implicit level 0 a path of this pass can reach (one push per bounce at most,
+// 63 in all: integrators.cpp:602) -- the stack planes are 2 bytes x slots each, so a 12-bounce pass gets 12 of them, not 63.
+// `records`: the two arrays only the per-sample records read.
+int ensure_state(bpt_ctx* ctx, bpt_ctx::Pipe* pp, uint32_t slots, uint32_t levels, bool records) {
     (void)ctx;
-    if (slots <= pp->max_slots) return BPT_OK;
+    if (slots <= pp->max_slots && levels <= pp->mstack_levels && (!records || pp->has_record_arrays)) return BPT_OK;
+    slots = std::max(slots, pp->max_slots); levels = std::max(levels, pp->mstack_levels); records = records || pp->has_record_arrays;
     free_all(&pp->allocs);
-    pp->max_slots = 0;
+    pp->max_slots = 0; pp->mstack_levels = 0; pp->has_record_arrays = false;
+    pp->st.primary_d = nullptr; pp->st.primary_o = nullptr;
     auto alloc = [&](void** p, size_t bytes) -> int {
         CK(cudaMalloc(p, bytes));
         pp->allocs.push_back(*p);
@@ -170,15 +176,17 @@ int ensure_state(bpt_ctx* ctx, bpt_ctx::Pipe* pp, uint32_t slots) {
     rc |= alloc((void**)&pp->st.prev_n, n*16);
     rc |= alloc((void**)&pp->st.jitter, n*8);
     rc |= alloc((void**)&pp->st.mstack_at, n);
-    rc |= alloc((void**)&pp->st.mstack, n*2*(BPT_MATERIAL_STACK_DEPTH - 1));     // level 0 ("air") is implicit
-    rc |= alloc((void**)&pp->st.primary_d, n*16);
-    rc |= alloc((void**)&pp->st.primary_o, n*16);
+    rc |= alloc((void**)&pp->st.mstack, n*2*std::max<uint32_t>(levels, 1));     // level 0 ("air") is implicit
+    if (records) {
+        rc |= alloc((void**)&pp->st.primary_d, n*16);
+        rc |= alloc((void**)&pp->st.primary_o, n*16);
+    }
     rc |= alloc((void**)&pp->q.active[0], n*4);
     rc |= alloc((void**)&pp->q.active[1], n*4);
     rc |= alloc((void**)&pp->q.shadow, n*sizeof(DShadowItem));
     rc |= alloc((void**)&pp->q.counters, 256);
     if (rc) return BPT_ERR_CUDA;
-    pp->max_slots = slots;
+    pp->max_slots = slots; pp->mstack_levels = levels; pp->has_record_arrays = records;
     return BPT_OK;
 }
 
@@ -795,11 +803,12 @@ retry_shape:
     uint64_t slots64 = (uint64_t)rect_w*rows_per_batch*S;
     if (slots64 > 0x7FFFFFFFull) { set_error("%s: batch too large", who); return BPT_ERR_ARG; }
     for (int p = 0; p < n_pipes; ++p) {
-        int rc = ensure_state(ctx, &ctx->pipes[p], (uint32_t)slots64);
+        const uint32_t levels = std::min<uint32_t>(BPT_MATERIAL_STACK_DEPTH - 1, std::max<uint32_t>(1, ctx->sc.settings.max_bounce_count));
+        int rc = ensure_state(ctx, &ctx->pipes[p], (uint32_t)slots64, levels, want_records);
         if (rc) {
             // out of device memory for this batch size: halve the batch and retry (the film/scene stay resident)
             cudaGetLastError();
-            for (auto& pp : ctx->pipes) { free_all(&pp.allocs); pp.max_slots = 0; }
+            for (auto& pp : ctx->pipes) { free_all(&pp.allocs); pp.max_slots = 0; pp.mstack_levels = 0; pp.has_record_arrays = false; }
             if (cap <= (1ull << 20)) return rc;
             cap >>= 1;
             goto retry_shape;
