@@ -157,6 +157,9 @@ struct TraceCounters {   // per-thread, flushed by the caller
 #ifndef BPT_TWO_LEVEL
 #define BPT_TWO_LEVEL 0           // 1: record roots fetch the near child's pair together with their own and take two levels per step
 #endif                            //    (measured on B200, C2: traversal 51.2 ms against 44.9 ms with one level per step -- see DESIGN.md)
+#ifndef BPT_COLD_LOCAL
+#define BPT_COLD_LOCAL 0          // 1: the per-ray state outside the inner loop lives in local memory instead of shared memory
+#endif
 #define BPT_TRACE_THREADS 128     // block size of every kernel that runs persistent_trace
 #ifndef BPT_TRIP_LIMIT
 #define BPT_TRIP_LIMIT (1u << 28) // scheduling-loop trips per warp; ~400x the largest legitimate count (a 64 Mi-slot batch)
@@ -170,6 +173,7 @@ enum { TRACE_MODE_CLOSEST = 0, TRACE_MODE_OCCLUSION = 1, TRACE_MODE_MIXED = 2 };
 // state would otherwise occupy registers the two-level node step needs for its loads.
 struct TraceShared {
     uint2    stack[BPT_SSTACK][BPT_TRACE_THREADS];   // {child ref, entry distance} of stack positions 0 .. BPT_SSTACK-1
+#if !BPT_COLD_LOCAL
     float    wray[6][BPT_TRACE_THREADS];             // the world-space ray (o, d) while the lane is inside a mesh BLAS
     uint32_t items_first[BPT_TRACE_THREADS];         // rest of the TLAS leaf's item loop, resumed when intersect_mesh "returns"
     uint32_t items_count[BPT_TRACE_THREADS];
@@ -180,6 +184,16 @@ struct TraceShared {
     float    hit_v[BPT_TRACE_THREADS], hit_w[BPT_TRACE_THREADS];
     uint32_t cur_prim[BPT_TRACE_THREADS];            // the instance whose BLAS the lane is in, and that mesh's first triangle
     uint32_t tri_base[BPT_TRACE_THREADS];
+#endif
+};
+
+// The same per-ray state as a per-thread record in LOCAL memory (-DBPT_COLD_LOCAL=1): touched a few times per ray, it then
+// occupies L1 lines only while in use instead of 8 KB of shared memory per CTA taken from the L1 carve-out for good.
+struct TraceCold {
+    float    wray[6];
+    uint32_t items_first, items_count, ignored, index, hit_prim, hit_tri;
+    float    hit_v, hit_w;
+    uint32_t cur_prim, tri_base;
 };
 
 // Persistent-warp traversal with lane refill and warp-level phase scheduling.
@@ -207,6 +221,16 @@ BPT_D void persistent_trace(const DScene& sc, Src& src, uint32_t n, uint32_t* cu
     __shared__ TraceShared sh;
     const uint32_t FULL = 0xFFFFFFFFu;
     const uint32_t tid = threadIdx.x, lane = tid & 31u;
+#if BPT_COLD_LOCAL
+    TraceCold cold_storage;
+    TraceCold* cold = &cold_storage;
+    asm volatile("" : "+l"(cold));              // opaque to the optimiser: the record stays in local memory, off the registers
+    #define COLD(f) (cold->f)
+    #define COLDW(k) (cold->wray[k])
+#else
+    #define COLD(f) (sh.f[tid])
+    #define COLDW(k) (sh.wray[k][tid])
+#endif
 
     RayT ray;                                   // the ray in the current space (world in the TLAS, object inside a BLAS)
     ray.o = v3(0.0f); ray.d = v3(0.0f); ray.inv = v3(0.0f); ray.neg = 0u;
@@ -235,7 +259,7 @@ BPT_D void persistent_trace(const DScene& sc, Src& src, uint32_t n, uint32_t* cu
         if (!(ref & BPT_WREF_LEAF)) { cur_a = ref; phase = P_INNER; return; }
         uint32_t count = (ref >> 28) & 7u, first = ref & BPT_WREF_INDEX_MASK;
         if (count == 0u) {                      // forced leaf with more than 7 items (bvh.cpp:254, :278): range is in the side table
-            uint32_t bb = blas_sp >= 0 ? __ldg(&sc.meshes[__ldg(&sc.primitives[sh.cur_prim[tid]].mesh)].big_base) : 0u;
+            uint32_t bb = blas_sp >= 0 ? __ldg(&sc.meshes[__ldg(&sc.primitives[COLD(cur_prim)].mesh)].big_base) : 0u;
             uint2 bl = __ldg(&sc.big_leaves[bb + first]);
             first = bl.x; count = bl.y;
         }
@@ -244,8 +268,8 @@ BPT_D void persistent_trace(const DScene& sc, Src& src, uint32_t n, uint32_t* cu
         else phase = P_ITEMS;
     };
     auto finish = [&]() {
-        HitRecord h; h.t = t; h.prim = sh.hit_prim[tid]; h.tri = sh.hit_tri[tid]; h.v = sh.hit_v[tid]; h.w = sh.hit_w[tid];
-        src.store(sh.index[tid], h);
+        HitRecord h; h.t = t; h.prim = COLD(hit_prim); h.tri = COLD(hit_tri); h.v = COLD(hit_v); h.w = COLD(hit_w);
+        src.store(COLD(index), h);
         phase = P_IDLE;
     };
     // the reference's "pop until a node survives its box re-test" (intersection.cpp:269-277, :450-454); when the stack is
@@ -272,14 +296,14 @@ BPT_D void persistent_trace(const DScene& sc, Src& src, uint32_t n, uint32_t* cu
         if (!tame) ray.neg &= ~BPT_RAY_TAME;    // node boxes beyond 1e15: every ray takes the exact compare+select slab test
         t = max_t;
         uint32_t hp = BPT_HIT_MISS;
-        sh.ignored[tid] = ignored_prim;
+        COLD(ignored) = ignored_prim;
         sp = 0; blas_sp = -1; pair_base = 0u;
         // planes first, linearly (intersection.cpp:424-433); in occlusion mode a plane hit does not return early
         for (uint32_t i = 0; i < sc.plane_count; ++i) {
             const DPlane& pl = sc.planes[i];
             if (plane_test(ray, v3(__ldg(&pl.n[0]), __ldg(&pl.n[1]), __ldg(&pl.n[2])), __ldg(&pl.d), t)) hp = BPT_HIT_PLANE | i;
         }
-        sh.hit_prim[tid] = hp; sh.hit_tri[tid] = 0xFFFFFFFFu; sh.hit_v[tid] = 0.0f; sh.hit_w[tid] = 0.0f;
+        COLD(hit_prim) = hp; COLD(hit_tri) = 0xFFFFFFFFu; COLD(hit_v) = 0.0f; COLD(hit_w) = 0.0f;
         float tn;
         bool hit = slab_any(ray, sc.tlas_root_q0, sc.tlas_root_q1, tn) && (tn < t);      // intersection.cpp:450-454
         if (STATS) ctr.tlas_pops += 1u;
@@ -335,7 +359,7 @@ BPT_D void persistent_trace(const DScene& sc, Src& src, uint32_t n, uint32_t* cu
                     bool is_occ = false;
                     src.load(idx, o, d, max_t, ign, is_occ);
                     occ = is_occ;
-                    sh.index[tid] = idx;
+                    COLD(index) = idx;
                     begin(o, d, max_t, ign);
                 }
             }
@@ -412,7 +436,7 @@ BPT_D void persistent_trace(const DScene& sc, Src& src, uint32_t n, uint32_t* cu
                 if (cur_b == 0u) {
                     pop_enter();
                 } else {
-                    const uint32_t slot = sh.tri_base[tid] + cur_a;
+                    const uint32_t slot = COLD(tri_base) + cur_a;
                     const DTriangle* tri = sc.triangles + slot;
                     const bool second = cur_b > 1u;
                     float4 a = __ldg(&tri->a_idx), e1 = __ldg(&tri->e1), e2 = __ldg(&tri->e2);
@@ -421,12 +445,12 @@ BPT_D void persistent_trace(const DScene& sc, Src& src, uint32_t n, uint32_t* cu
                     bool stop = false;
                     float v, w;
                     if (triangle_test(ray, v3(a), v3(e1), v3(e2), t, v, w)) {
-                        sh.hit_tri[tid] = slot; sh.hit_prim[tid] = sh.cur_prim[tid]; sh.hit_v[tid] = v; sh.hit_w[tid] = w;
+                        COLD(hit_tri) = slot; COLD(hit_prim) = COLD(cur_prim); COLD(hit_v) = v; COLD(hit_w) = w;
                         if (occlusion()) { finish(); stop = true; }
                     }
                     if (!stop && second) {
                         if (triangle_test(ray, v3(a2), v3(e12), v3(e22), t, v, w)) {
-                            sh.hit_tri[tid] = slot + 1u; sh.hit_prim[tid] = sh.cur_prim[tid]; sh.hit_v[tid] = v; sh.hit_w[tid] = w;
+                            COLD(hit_tri) = slot + 1u; COLD(hit_prim) = COLD(cur_prim); COLD(hit_v) = v; COLD(hit_w) = w;
                             if (occlusion()) { finish(); stop = true; }
                         }
                     }
@@ -447,10 +471,10 @@ BPT_D void persistent_trace(const DScene& sc, Src& src, uint32_t n, uint32_t* cu
                     // the world ray again: same values from the same operations.  (Keeping 1/d and the sign bits in shared
                     // memory instead of re-dividing was measured: 44.3 against 43.6 ms of traversal on C2 -- the 2 KB more of
                     // shared memory per CTA cost more L1 than the three divisions cost issue slots.)
-                    make_ray(ray, v3(sh.wray[0][tid], sh.wray[1][tid], sh.wray[2][tid]),
-                                  v3(sh.wray[3][tid], sh.wray[4][tid], sh.wray[5][tid]));
+                    make_ray(ray, v3(COLDW(0), COLDW(1), COLDW(2)),
+                                  v3(COLDW(3), COLDW(4), COLDW(5)));
                     if (!tame) ray.neg &= ~BPT_RAY_TAME;
-                    cur_a = sh.items_first[tid]; cur_b = sh.items_count[tid];
+                    cur_a = COLD(items_first); cur_b = COLD(items_count);
                     phase = P_ITEMS;
                 } else {
                     finish();                   // the TLAS stack is empty: intersect_scene_internal returns
@@ -462,7 +486,7 @@ BPT_D void persistent_trace(const DScene& sc, Src& src, uint32_t n, uint32_t* cu
                 } else {
                     uint32_t prim_index = __ldg(&sc.tlas_indices[cur_a]);
                     ++cur_a; --cur_b;
-                    if (prim_index != sh.ignored[tid]) {
+                    if (prim_index != COLD(ignored)) {
                         const DPrimitive* prim = sc.primitives + prim_index;
                         float4 m[3] = {__ldg(&prim->inv[0]), __ldg(&prim->inv[1]), __ldg(&prim->inv[2])};
                         RayT oray;
@@ -476,12 +500,12 @@ BPT_D void persistent_trace(const DScene& sc, Src& src, uint32_t n, uint32_t* cu
                         }
                         if (type == BPT_PRIM_SPHERE) {
                             if (sphere_test(oray, __ldg(&prim->sphere_r), t)) {
-                                sh.hit_prim[tid] = prim_index; sh.hit_tri[tid] = 0xFFFFFFFFu;
+                                COLD(hit_prim) = prim_index; COLD(hit_tri) = 0xFFFFFFFFu;
                                 if (occlusion()) finish();
                             }
                         } else if (type == BPT_PRIM_BOX) {
                             if (box_test(oray, __ldg(&prim->box_r[0]), __ldg(&prim->box_r[1]), __ldg(&prim->box_r[2]), t)) {
-                                sh.hit_prim[tid] = prim_index; sh.hit_tri[tid] = 0xFFFFFFFFu;
+                                COLD(hit_prim) = prim_index; COLD(hit_tri) = 0xFFFFFFFFu;
                                 if (occlusion()) finish();
                             }
                         } else if (type == BPT_PRIM_MESH) {
@@ -492,13 +516,13 @@ BPT_D void persistent_trace(const DScene& sc, Src& src, uint32_t n, uint32_t* cu
                             bool root_hit = slab_any(oray, q0, q1, tn) && (tn < t);          // intersect_mesh pops its root first (:269-277)
                             if (root_hit) {
                                 // intersect_mesh is "called": park the world-level state, switch to the object-space ray
-                                sh.wray[0][tid] = ray.o.x; sh.wray[1][tid] = ray.o.y; sh.wray[2][tid] = ray.o.z;
-                                sh.wray[3][tid] = ray.d.x; sh.wray[4][tid] = ray.d.y; sh.wray[5][tid] = ray.d.z;
-                                sh.items_first[tid] = cur_a; sh.items_count[tid] = cur_b;
+                                COLDW(0) = ray.o.x; COLDW(1) = ray.o.y; COLDW(2) = ray.o.z;
+                                COLDW(3) = ray.d.x; COLDW(4) = ray.d.y; COLDW(5) = ray.d.z;
+                                COLD(items_first) = cur_a; COLD(items_count) = cur_b;
                                 ray = oray; blas_sp = sp;
                                 pair_base = __ldg(&mesh->pair_base);
-                                sh.tri_base[tid] = __ldg(&mesh->tri_base);
-                                sh.cur_prim[tid] = prim_index;
+                                COLD(tri_base) = __ldg(&mesh->tri_base);
+                                COLD(cur_prim) = prim_index;
                                 enter(__float_as_uint(q1.z));
                             } else if (STATS) {
                                 ctr.blas_pops += 1u;
@@ -512,6 +536,8 @@ BPT_D void persistent_trace(const DScene& sc, Src& src, uint32_t n, uint32_t* cu
 #ifndef BPT_DBG_PLAIN_LOOP
     if (trips == BPT_TRIP_LIMIT) *sc.error_flag = BPT_DEVERR_TRIP_LIMIT;
 #endif
+    #undef COLD
+    #undef COLDW
 }
 
 } // namespace bpt
