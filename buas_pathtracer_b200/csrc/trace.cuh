@@ -157,6 +157,12 @@ struct TraceCounters {   // per-thread, flushed by the caller
 #ifndef BPT_TWO_LEVEL
 #define BPT_TWO_LEVEL 0           // 1: record roots fetch the near child's pair together with their own and take two levels per step
 #endif                            //    (measured on B200, C2: traversal 51.2 ms against 44.9 ms with one level per step -- see DESIGN.md)
+#ifndef BPT_KEEP_EIGHTHS
+#define BPT_KEEP_EIGHTHS 2        // the node phase keeps running while at least this many eighths of the lanes that started it still want it
+#endif                            // (C2 traversal ms at 0..6 eighths: 45.5 / 42.3 / 41.2 / 41.5 / 42.1 / 43.0 / 43.7; round 1 used 6)
+#ifndef BPT_KEEP_TRI_EIGHTHS
+#define BPT_KEEP_TRI_EIGHTHS 0    // the triangle phase runs until no lane wants it (C2 traversal ms at 0 / 1 / 2 / 4 / 6 eighths: 41.1 / 41.3 / 41.4 / 42.1 / 43.1)
+#endif
 #ifndef BPT_COLD_LOCAL
 #define BPT_COLD_LOCAL 0          // 1: the per-ray state outside the inner loop lives in local memory instead of shared memory
 #endif
@@ -366,8 +372,9 @@ BPT_D void persistent_trace(const DScene& sc, Src& src, uint32_t n, uint32_t* cu
             if (base + nid >= n) exhausted = true;
           }
         } else if (run == P_INNER) {
-          // stay in this phase while at least 3/4 of the lanes that started it still want it (1 vote instead of 4)
-          uint32_t keep = max(best - (best >> 2), 1u);
+          // stay in this phase while at least BPT_KEEP_EIGHTHS/8 of the lanes that started it still want it (one ballot per
+          // step instead of the full vote; measured on C2: 6/8 -> 43.7 ms of traversal, 2/8 -> 41.2)
+          uint32_t keep = max((best*BPT_KEEP_EIGHTHS + 7u) >> 3, 1u);
           do {
             if (phase == P_INNER) {
                 // the node's split axis and the ray's sign say which child is near (intersection.cpp:303-318): known
@@ -429,7 +436,7 @@ BPT_D void persistent_trace(const DScene& sc, Src& src, uint32_t n, uint32_t* cu
             }
           } while (__popc(__ballot_sync(FULL, phase == P_INNER)) >= keep);
         } else if (run == P_TRI) {
-          uint32_t keep = max(best - (best >> 2), 1u);
+          uint32_t keep = max((best*BPT_KEEP_TRI_EIGHTHS + 7u) >> 3, 1u);
           do {
             if (phase == P_TRI) {
                 // up to two triangles of the leaf per step, fetched together, tested in the reference's order
@@ -481,9 +488,7 @@ BPT_D void persistent_trace(const DScene& sc, Src& src, uint32_t n, uint32_t* cu
                 }
             }
             if (phase == P_ITEMS) {
-                if (cur_b == 0u) {
-                    pop_enter();
-                } else {
+                if (cur_b != 0u) {
                     uint32_t prim_index = __ldg(&sc.tlas_indices[cur_a]);
                     ++cur_a; --cur_b;
                     if (prim_index != COLD(ignored)) {
@@ -529,6 +534,13 @@ BPT_D void persistent_trace(const DScene& sc, Src& src, uint32_t n, uint32_t* cu
                             }
                         }
                     }
+                }
+                // The leaf's items are used up (and the lane neither entered a BLAS nor finished on an occlusion hit): the
+                // reference's item loop ends and its node loop pops the next TLAS node.  An empty TLAS stack ends the ray
+                // right here, in the same step, instead of parking the lane for two more scheduling rounds.
+                if (phase == P_ITEMS && cur_b == 0u) {
+                    pop_enter();
+                    if (phase == P_RET && blas_sp < 0) finish();
                 }
             }
         }
