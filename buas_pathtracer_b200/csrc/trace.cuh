@@ -163,6 +163,9 @@ struct TraceCounters {   // per-thread, flushed by the caller
 #ifndef BPT_KEEP_TRI_EIGHTHS
 #define BPT_KEEP_TRI_EIGHTHS 0    // the triangle phase runs until no lane wants it (C2 traversal ms at 0 / 1 / 2 / 4 / 6 eighths: 41.1 / 41.3 / 41.4 / 42.1 / 43.1)
 #endif
+#ifndef BPT_KEEP_ITEMS_EIGHTHS
+#define BPT_KEEP_ITEMS_EIGHTHS 2  // the TLAS-item / return phase keeps running like the other phases when the TLAS has inner nodes (C3 / C4:
+#endif                            // -3 % traversal time); with a TLAS that is a single leaf (C2) it runs one step per vote (the loop costs +0.8 % there)
 #ifndef BPT_COLD_LOCAL
 #define BPT_COLD_LOCAL 0          // 1: the per-ray state outside the inner loop lives in local memory instead of shared memory
 #endif
@@ -251,6 +254,7 @@ BPT_D void persistent_trace(const DScene& sc, Src& src, uint32_t n, uint32_t* cu
     int phase = P_IDLE;
     bool exhausted = false;
     const bool tame = sc.tame_bounds != 0;
+    const bool tlas_flat = (__float_as_uint(sc.tlas_root_q1.z) & BPT_WREF_LEAF) != 0u;     // the whole TLAS is one leaf
     auto occlusion = [&]() { return MODE == TRACE_MODE_MIXED ? occ : (MODE == TRACE_MODE_OCCLUSION); };
 
     auto push = [&](uint32_t ref, float tn) {
@@ -470,6 +474,8 @@ BPT_D void persistent_trace(const DScene& sc, Src& src, uint32_t n, uint32_t* cu
             }
           } while (__popc(__ballot_sync(FULL, phase == P_TRI)) >= keep);
         } else {
+          uint32_t keep = tlas_flat ? 33u : max((best*BPT_KEEP_ITEMS_EIGHTHS + 7u) >> 3, 1u);
+          do {
             if (phase == P_RET) {
                 if (blas_sp >= 0) {
                     // intersect_mesh returns: back to the world-space ray and the TLAS leaf's item loop
@@ -543,6 +549,7 @@ BPT_D void persistent_trace(const DScene& sc, Src& src, uint32_t n, uint32_t* cu
                     if (phase == P_RET && blas_sp < 0) finish();
                 }
             }
+          } while (__popc(__ballot_sync(FULL, phase >= P_ITEMS)) >= keep);
         }
     }
 #ifndef BPT_DBG_PLAIN_LOOP
