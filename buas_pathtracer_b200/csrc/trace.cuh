@@ -163,6 +163,12 @@ struct TraceCounters {   // per-thread, flushed by the caller
 #ifndef BPT_KEEP_TRI_EIGHTHS
 #define BPT_KEEP_TRI_EIGHTHS 0    // the triangle phase runs until no lane wants it (C2 traversal ms at 0 / 1 / 2 / 4 / 6 eighths: 41.1 / 41.3 / 41.4 / 42.1 / 43.1)
 #endif
+#ifndef BPT_TRI_BIAS
+#define BPT_TRI_BIAS 1            // phase selection weighs the lanes waiting for triangles (and for TLAS items: BPT_ITEMS_BIAS) by this factor
+#endif
+#ifndef BPT_ITEMS_BIAS
+#define BPT_ITEMS_BIAS 1
+#endif
 #ifndef BPT_KEEP_ITEMS_EIGHTHS
 #define BPT_KEEP_ITEMS_EIGHTHS 2  // the TLAS-item / return phase keeps running like the other phases when the TLAS has inner nodes (C3 / C4:
 #endif                            // -3 % traversal time); with a TLAS that is a single leaf (C2) it runs one step per vote (the loop costs +0.8 % there)
@@ -341,10 +347,10 @@ BPT_D void persistent_trace(const DScene& sc, Src& src, uint32_t n, uint32_t* cu
         uint32_t n_inner = (counts >> 8) & 0xFFu, n_tri = (counts >> 16) & 0xFFu, n_items = counts >> 24;
         uint32_t n_idle = counts & 0xFFu;
 
-        int run = P_INNER; uint32_t best = n_inner;
-        if (n_tri > best)   { best = n_tri;   run = P_TRI; }
-        if (n_items > best) { best = n_items; run = P_ITEMS; }
-        if (n_idle >= refill || n_idle > best) { run = P_IDLE; }
+        int run = P_INNER; uint32_t best = n_inner, score = n_inner;
+        if (n_tri*BPT_TRI_BIAS > score)     { best = n_tri;   score = n_tri*BPT_TRI_BIAS;     run = P_TRI; }
+        if (n_items*BPT_ITEMS_BIAS > score) { best = n_items; score = n_items*BPT_ITEMS_BIAS; run = P_ITEMS; }
+        if (n_idle >= refill || n_idle > score) { run = P_IDLE; }
 
         if (run == P_IDLE) {
           if constexpr (LOCAL) {
