@@ -164,7 +164,9 @@ struct TraceCounters {   // per-thread, flushed by the caller
 #define BPT_KEEP_TRI_EIGHTHS 0    // the triangle phase runs until no lane wants it (C2 traversal ms at 0 / 1 / 2 / 4 / 6 eighths: 41.1 / 41.3 / 41.4 / 42.1 / 43.1)
 #endif
 #ifndef BPT_TRI_BIAS
-#define BPT_TRI_BIAS 1            // phase selection weighs the lanes waiting for triangles (and for TLAS items: BPT_ITEMS_BIAS) by this factor
+#define BPT_TRI_BIAS 4            // phase selection weighs the lanes waiting for triangles by this factor: a leaf is at most two short steps and its lanes
+                                  // come back to the node phase, whose long runs then start fuller (C2 traversal ms at 1 / 2 / 3 / 4 / 8 / 32: 40.5 / 39.3 /
+                                  // 38.9 / 38.8 / 38.7 / 38.7; C3 best at 3-4).  The same weight on TLAS items (BPT_ITEMS_BIAS) loses.
 #endif
 #ifndef BPT_ITEMS_BIAS
 #define BPT_ITEMS_BIAS 1
