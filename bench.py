@@ -252,10 +252,12 @@ def main():
         r.render_pass_bands(n_spp, bands, frame_count=frame_count)   # this rank's row blocks as one workload
 
     def step(frame_count):
+        # One progressive pass (+ its reduce), enqueued; the host does not wait per step, like the reference's render loop
+        # that starts the next pass as soon as the previous one is handed to the display (raytracer.cpp:692-757).  The
+        # library orders what must be ordered on the device: pass k+1's splats wait for pass k's reduce / film readers.
         render(frame_count)
         if comm is not None:
             r.reduce_film(comm, 0)                         # one collective per progressive pass, behind the pass on its stream
-        r.sync()
 
     # --- multi-GPU correctness on the hardware (untimed): the N-rank reduced film against rank 0 rendering the whole
     #     frame alone, same seeds; they differ only in the order of float additions (atomics + the reduce)
@@ -289,8 +291,9 @@ def main():
     r.stats_enable(False)
     r.film_clear()
 
-    for i in range(args.warmup):
+    for i in range(args.warmup):                      # enqueued back to back like the timed steps (same batch shapes, path state allocated)
         step(i * spp)
+    r.sync()
     r.film_clear()
     r.sync()
     torch.cuda.synchronize()
@@ -308,6 +311,7 @@ def main():
     launches = trace_launches = 0
     for i in range(args.steps):
         step(0)                                       # same frame_count -> same rays as the counting pass
+    r.sync()                                          # the library renders on its own streams: wait for all K steps, then stamp
     ev1.record()
     torch.cuda.synchronize()
     if dist is not None:

@@ -98,6 +98,19 @@ struct bpt_ctx {
     uint32_t merge_max_slots = 16u << 20; // batches larger than this trace the two populations separately             // trace bounce b's extension rays and bounce b-1's shadow rays in one launch
     int32_t* d_row_map = nullptr;
     uint32_t row_map_capacity = 0;
+    std::vector<int32_t> row_map_host;    // what d_row_map holds: a pass over the same rows as the last one uploads nothing
+    // Consecutive passes overlap: the pipelines of pass k+1 start while pass k's last batches are still in their kernel
+    // tails.  Only what touches the film is ordered across passes -- a k_splat of pass k+1 waits for `film_free`, recorded
+    // on ctx->stream behind the join of pass k and behind every reader / clear of the film enqueued since.
+    cudaEvent_t film_free = nullptr;
+    bool pipes_need_setup = true;         // something the pipelines read was enqueued on ctx->stream (row map, scene flip): they wait for it once
+    bool last_pass_single = false;
+    // Batch -> stream round-robin continues across passes: consecutive one-batch passes alternate between the batch
+    // streams, so pass k+1's full-machine launches run underneath the chain of small launches (each as long as its
+    // longest ray) that ends pass k.  Making a batch wait until the one before it is past its bulk (an event behind the
+    // shading of bounce 0 / 1 / 2) was measured and is not needed: the streams fall out of step by themselves, one
+    // persistent kernel at a time (8-rank share of C2: 7.57 ms with or without; C2 full frame 54.0 without, 54.2-54.4 with).
+    uint64_t batch_serial = 0;
 
     DStats* d_stats = nullptr;
     bool stats_enabled = false;
@@ -245,6 +258,9 @@ int flip_to_pending_scene(bpt_ctx* ctx) {
     if (!ctx->pending) return BPT_OK;
     int target = 1 - ctx->active_set;
     CK(cudaStreamWaitEvent(ctx->stream, ctx->sets[target].uploaded, 0));
+    // the batch streams wait for the upload itself, not for ctx->stream (which carries the join of the previous pass): the
+    // first batch over the new scene overlaps the last batch over the old one
+    for (auto& pp : ctx->pipes) CK(cudaStreamWaitEvent(pp.stream, ctx->sets[target].uploaded, 0));
     DScene n = ctx->pending_sc;
     n.strata_perm = ctx->sc.strata_perm; n.bn_sobol = ctx->sc.bn_sobol; n.bn_scramble = ctx->sc.bn_scramble; n.bn_rank = ctx->sc.bn_rank;
     n.error_flag = ctx->sc.error_flag;
@@ -320,6 +336,7 @@ int bpt_create(int device, bpt_ctx** out_ctx) {
     *ctx->h_error = BPT_DEVERR_NONE;
     CK(cudaHostGetDevicePointer((void**)&ctx->sc.error_flag, ctx->h_error, 0));
     CK(cudaEventCreate(&ctx->pass_begin));
+    CK(cudaEventCreateWithFlags(&ctx->film_free, cudaEventDisableTiming));
     CK(cudaEventCreate(&ctx->pass_end));
     {
         int a = 0, b = 0;
@@ -376,7 +393,7 @@ void bpt_destroy(bpt_ctx* ctx) {
     if (ctx->h_error) cudaFreeHost(ctx->h_error);
     cudaFree(ctx->d_perm); cudaFree(ctx->d_sobol); cudaFree(ctx->d_scramble); cudaFree(ctx->d_rank);
     for (auto& s : ctx->spans) { cudaEventDestroy(s.a); cudaEventDestroy(s.b); }
-    cudaEventDestroy(ctx->pass_begin); cudaEventDestroy(ctx->pass_end);
+    cudaEventDestroy(ctx->pass_begin); cudaEventDestroy(ctx->pass_end); cudaEventDestroy(ctx->film_free);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -776,6 +793,15 @@ static int render_rows(bpt_ctx* ctx, int32_t x0, int32_t x1, const std::vector<i
     uint32_t S, rows_per_batch;
     uint64_t n_batches;
     const int n_pipes_wanted = n_pipes;
+    // The caller enqueues passes back to back (the previous one has not finished): a pass that fits one batch stays one
+    // batch -- half the launches, half the kernel tails -- and consecutive passes alternate between the batch streams.
+    // A caller that waits for every pass gets the pass split over the streams instead, so that they overlap inside it.
+    bool back_to_back = false;
+    if (n_pipes > 1 && ctx->pass_recorded && !ctx->last_pass_single) {
+        back_to_back = cudaEventQuery(ctx->pass_end) == cudaErrorNotReady;
+        cudaGetLastError();
+    }
+    if (const char* e = getenv("BPT_BACK_TO_BACK")) back_to_back = atoi(e) != 0 && n_pipes > 1;
 retry_shape:
     n_pipes = n_pipes_wanted;             // a retry changes the batch count, and with it how many pipelines can be fed
     S = (uint32_t)std::min<uint64_t>(spp, std::max<uint64_t>(1, cap / rect_w));
@@ -785,7 +811,7 @@ retry_shape:
         // fewer batches than pipelines cannot overlap: split the rows so that every pipeline gets a batch and the
         // pipelines hide each other's kernel tails (only worth it when each batch still fills the machine)
         uint64_t row_batches = (rect_h + rows_per_batch - 1)/rows_per_batch;
-        uint64_t want = std::max<uint64_t>(ctx->min_batches, (uint64_t)n_pipes);
+        uint64_t want = std::max<uint64_t>(ctx->min_batches, back_to_back ? 1u : (uint64_t)n_pipes);
         uint64_t total = (uint64_t)rect_w*rect_h*spp;
         while (want > 1 && total/want < (1ull << 20) && want > ctx->min_batches) --want;
         if (S == spp && row_batches < want && rect_h >= want) {
@@ -793,8 +819,8 @@ retry_shape:
             n_batches = (rect_h + rows_per_batch - 1)/rows_per_batch;
         }
     }
-    if (n_batches < (uint64_t)n_pipes) n_pipes = (int)n_batches;
-    if (n_pipes >= 2) {
+    if (n_batches < (uint64_t)n_pipes && !back_to_back) n_pipes = (int)n_batches;
+    if (n_pipes >= 2 && n_batches > 1) {
         // even out the batches of the last round over the pipelines
         uint32_t nb = (rect_h + rows_per_batch - 1)/rows_per_batch;
         uint32_t rounded = ((nb + n_pipes - 1)/n_pipes)*n_pipes;
@@ -827,21 +853,36 @@ retry_shape:
         }
     }
 
+    // The pipelines read: the scene set (flip_to_pending_scene), the row map, the sampler tables -- all enqueued on
+    // ctx->stream.  A pass that finds them unchanged does not wait for ctx->stream at all, so its first batches overlap
+    // the kernel tails of the previous pass (ctx->stream carries that pass's join).  The one-batch-at-a-time mode
+    // (per-stage timing, records) keeps the full join on both sides so that its spans measure one kernel each.
+    const bool single = ctx->detailed_timing || want_records;
     if (ctx->row_map_capacity < rect_h) {
         CK(cudaStreamSynchronize(ctx->stream));
         for (auto& pp : ctx->pipes) CK(cudaStreamSynchronize(pp.stream));
         cudaFree(ctx->d_row_map); ctx->d_row_map = nullptr; ctx->row_map_capacity = 0;
         CK(cudaMalloc((void**)&ctx->d_row_map, (size_t)std::max<uint32_t>(rect_h, 4096)*sizeof(int32_t)));
         ctx->row_map_capacity = std::max<uint32_t>(rect_h, 4096);
+        ctx->row_map_host.clear();
     }
-    // the previous pass may still be reading the old row map on the pipe streams: order the copy after them
-    for (int p = 0; p < BPT_MAX_PIPES; ++p) { CK(cudaEventRecord(ctx->pipes[p].done, ctx->pipes[p].stream)); CK(cudaStreamWaitEvent(ctx->stream, ctx->pipes[p].done, 0)); }
-    CK(cudaMemcpyAsync(ctx->d_row_map, rows.data(), (size_t)rect_h*sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+    if (ctx->row_map_host != rows) {
+        // the previous pass may still be reading the old row map on the pipe streams: order the copy after them
+        for (int p = 0; p < BPT_MAX_PIPES; ++p) { CK(cudaEventRecord(ctx->pipes[p].done, ctx->pipes[p].stream)); CK(cudaStreamWaitEvent(ctx->stream, ctx->pipes[p].done, 0)); }
+        ctx->row_map_host = rows;         // the async copy below reads this vector: it stays untouched until the next change, which joins first
+        CK(cudaMemcpyAsync(ctx->d_row_map, ctx->row_map_host.data(), (size_t)rect_h*sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+        ctx->pipes_need_setup = true;
+    }
 
     ctx->spans_used = 0;
     ctx->launches = 0; ctx->trace_launches = 0;
-    CK(cudaEventRecord(ctx->pass_begin, ctx->stream));
-    for (int p = 0; p < n_pipes; ++p) CK(cudaStreamWaitEvent(ctx->pipes[p].stream, ctx->pass_begin, 0));
+    CK(cudaEventRecord(ctx->pass_begin, ctx->stream));      // with overlapping passes: the end of the previous pass, so total_ms is the pass period
+    if (ctx->pipes_need_setup || single || ctx->last_pass_single) {
+        for (int p = 0; p < BPT_MAX_PIPES; ++p) CK(cudaStreamWaitEvent(ctx->pipes[p].stream, ctx->pass_begin, 0));
+        ctx->pipes_need_setup = false;
+    }
+    ctx->last_pass_single = single;
+    CK(cudaEventRecord(ctx->film_free, ctx->stream));
     const bool stats = ctx->stats_enabled;
     uint32_t max_bounce = sc.settings.max_bounce_count;
     if (sc.settings.integrator == BPT_INTEGRATOR_NORMALS || sc.settings.integrator == BPT_INTEGRATOR_DISTANCES) max_bounce = 1;   // one intersect_scene per sample
@@ -850,7 +891,8 @@ retry_shape:
     for (uint32_t sa = 0; sa < spp; sa += S) {
         uint32_t Sb = std::min(S, spp - sa);
         for (uint32_t row = 0; row < rect_h; row += rows_per_batch, ++batch_index) {
-            bpt_ctx::Pipe& pp = ctx->pipes[batch_index % n_pipes];
+            const int pipe_index = single ? 0 : (int)(ctx->batch_serial++ % (uint64_t)n_pipes);
+            bpt_ctx::Pipe& pp = ctx->pipes[pipe_index];
             cudaStream_t s = pp.stream;
             BatchDesc b;
             b.x0 = x0; b.row0 = row; b.row_map = ctx->d_row_map;
@@ -934,6 +976,7 @@ retry_shape:
                 }
             }
 
+            CK(cudaStreamWaitEvent(s, ctx->film_free, 0));    // the film's readers / clears enqueued before this pass (and the previous pass itself) are through
             begin_span(ctx, ST_SPLAT, s);
             uint32_t pixels = rect_w*b.rows;
             if (sc.filter_lut_size != 0 && sc.filter_radius == 2) {
@@ -955,7 +998,7 @@ retry_shape:
             }
         }
     }
-    for (int p = 0; p < n_pipes; ++p) {
+    for (int p = 0; p < BPT_MAX_PIPES; ++p) {          // the join: what follows on ctx->stream (film readers, the next upload's last_use) sees the whole pass
         CK(cudaEventRecord(ctx->pipes[p].done, ctx->pipes[p].stream));
         CK(cudaStreamWaitEvent(ctx->stream, ctx->pipes[p].done, 0));
     }

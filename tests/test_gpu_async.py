@@ -77,3 +77,36 @@ def test_download_async_snapshot_is_not_disturbed_by_the_next_pass(bpt):
     assert float(both[..., 3].sum()) > 1.9 * float(first[..., 3].sum())
     r.host_unregister(out)
     r.close()
+
+
+def test_back_to_back_passes_equal_synchronised_passes(bpt):
+    """Passes enqueued without waiting overlap on the device (the next pass's batches start under the previous pass's
+    kernel tails, consecutive one-batch passes alternate between the batch streams).  What touches the film stays ordered:
+    the snapshot taken behind pass k holds passes 0..k exactly -- nothing of pass k+1."""
+    w, h, spp, passes = 320, 180, 8, 6
+    s = bpt.Scene(); scenes.c2_icosphere(s, w, h, level=5)
+    r = bpt.Renderer(0)
+    r.upload_scene(s)
+    r.film_resize(w, h)
+    want = []
+    for p in range(passes):                       # the synchronous schedule: wait for every pass
+        r.render_pass(spp, frame_count=p * spp)
+        want.append(r.download_film())
+    assert float(want[1][..., 3].sum()) > 1.9 * float(want[0][..., 3].sum())
+    outs = [np.zeros((h, w, 4), np.float32) for _ in range(passes)]
+    for o in outs:
+        r.host_register(o)
+    for rep in range(2):                          # the second round runs with the path state of both streams allocated
+        r.film_clear()
+        for p in range(passes):
+            r.render_pass(spp, frame_count=p * spp)
+            r.download_film_async(outs[p])
+            if p == 2:
+                r.wait_download()                 # a host wait in the middle of the loop changes nothing either
+        r.wait_download()
+        r.sync()
+        for p in range(passes):
+            assert np.allclose(outs[p], want[p], rtol=1e-5, atol=1e-6), (rep, p)
+    for o in outs:
+        r.host_unregister(o)
+    r.close()

@@ -35,6 +35,7 @@ def test_two_rank_reduced_film_equals_single_gpu_film(bpt, recipe, kw):
     rs = [bpt.Renderer(d) for d in range(world)]
     comms = lib.nccl_comm_init_all(list(range(world)))
     errors = []
+    per_pass = [np.zeros((h, w, 4), np.float32) for _ in range(passes)]
 
     def rank_main(rank):
         try:
@@ -44,6 +45,10 @@ def test_two_rank_reduced_film_equals_single_gpu_film(bpt, recipe, kw):
             for p in range(passes):                 # progressive: the partial films keep accumulating, every pass ends in a reduce
                 r.render_pass_bands(spp, _bands(h, rank, world), frame_count=p * spp)
                 r.reduce_film(comms[rank], 0)
+                if rank == 0:
+                    r.download_film_async(per_pass[p], reduced=True)    # the next pass is enqueued right behind: it must not leak into this image
+            if rank == 0:
+                r.wait_download()
             r.sync()
         except Exception as e:                      # noqa: BLE001
             errors.append(e)
@@ -60,7 +65,8 @@ def test_two_rank_reduced_film_equals_single_gpu_film(bpt, recipe, kw):
     r.film_clear()
     for p in range(passes):
         r.render_pass(spp, frame_count=p * spp)
-    alone = r.download_film()
+        alone = r.download_film()
+        assert np.allclose(per_pass[p], alone, rtol=1e-4, atol=1e-5), (p, float(np.max(np.abs(per_pass[p] - alone))))
     assert np.all(alone[..., 3] > 0)
     assert np.allclose(reduced, alone, rtol=1e-4, atol=1e-5), float(np.max(np.abs(reduced - alone)))
     for c, rr in zip(comms, rs):
