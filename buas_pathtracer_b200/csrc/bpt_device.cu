@@ -35,7 +35,7 @@ struct TimedSpan { cudaEvent_t a, b; int stage; };
 struct bpt_ctx {
     int device = 0;
     int sm_count = 148;
-    uint32_t refill = 16;                 // persistent warps fetch new rays once this many lanes are idle (or idle is the largest group); 12-24 measured +1.5 % over 8 with 8 CTAs/SM
+    uint32_t refill = 16;                 // persistent warps fetch new rays once this many lanes are idle (or idle is the largest group); round 1: 12-24 +1.5 % over 8; round 2: 8-33 within 0.3 %
     int trace_ctas_per_sm = 8;            // resident CTAs of the persistent traversal kernels (occupancy query)
     cudaStream_t stream = nullptr;
 
@@ -901,6 +901,7 @@ retry_shape:
             b.frame_count = frame_count; b.salt = seed_salt;
             b.slots = rect_w*b.rows*Sb;
             b.want_records = want_records ? 1u : 0u;
+            set_batch_magic(b);
 
             begin_span(ctx, ST_RAYGEN, s);
             k_raygen<<<grid_for(ctx, b.slots, 256, 8), 256, 0, s>>>(sc, pp.st, b);

@@ -6,6 +6,20 @@
 
 namespace bpt {
 
+// Path-state accesses.  Every array is streamed -- written by one kernel, read once by the next -- while the BVH nodes and
+// triangles the traversal kernels walk are re-read all the time: -DBPT_STREAM_HINTS=1 marks the path-state traffic
+// evict-first (ld.global.cs / st.global.cs) so that it does not push the scene out of L2.
+#ifndef BPT_STREAM_HINTS
+#define BPT_STREAM_HINTS 0
+#endif
+#if BPT_STREAM_HINTS
+#define PSL(p) __ldcs(p)
+#define PSS(p, v) __stcs((p), (v))
+#else
+#define PSL(p) (*(p))
+#define PSS(p, v) (*(p) = (v))
+#endif
+
 // One batch = pixel rows [ya, yb) of the pass rect x samples [sa, sb).  slot = (row-major pixel in batch)*S + (s - sa)
 struct BatchDesc {
     int32_t  x0;              // first pixel column of the rect
@@ -17,16 +31,24 @@ struct BatchDesc {
     uint32_t salt;
     uint32_t slots;           // rect_w*rows*S
     uint32_t want_records;
+    uint32_t magic_S, magic_w;   // udiv_magic multipliers of S and rect_w (set_batch_magic)
 };
 
+inline void set_batch_magic(BatchDesc& b) {
+    auto magic = [](uint32_t d) { uint64_t m = (1ull << 32)/d; return (uint32_t)(m > 0xFFFFFFFFull ? 0xFFFFFFFFull : m); };
+    b.magic_S = magic(b.S); b.magic_w = magic(b.rect_w);
+}
+
 BPT_D SamplerCtx make_sampler(const DScene& sc, const BatchDesc& b, uint32_t slot) {
-    uint32_t pix = slot / b.S, s = slot - pix*b.S;
+    uint32_t s, px;
+    uint32_t pix = udiv_magic(slot, b.S, b.magic_S, s);
+    uint32_t row = udiv_magic(pix, b.rect_w, b.magic_w, px);
     SamplerCtx c;
     c.strata_perm = sc.strata_perm; c.bn_sobol = sc.bn_sobol; c.bn_scramble = sc.bn_scramble; c.bn_rank = sc.bn_rank;
     c.strategy = sc.settings.sampling_strategy;
     c.index = b.frame_count + b.sa + s;
-    c.x = (uint32_t)(b.x0 + (int32_t)(pix % b.rect_w));
-    c.y = (uint32_t)__ldg(&b.row_map[b.row0 + pix / b.rect_w]);
+    c.x = (uint32_t)(b.x0 + (int32_t)px);
+    c.y = (uint32_t)__ldg(&b.row_map[b.row0 + row]);
     return c;
 }
 
@@ -279,9 +301,9 @@ k_raygen(DScene sc, DPathState st, BatchDesc b) {
         V3 ray_o = lens_p;
         V3 ray_d = normalize(film_p - lens_p);
 
-        st.ray_o[slot] = make_float4(ray_o.x, ray_o.y, ray_o.z, 3.402823466e+38f);    // make_ray's FLT_MAX far clip
-        st.ray_d[slot] = make_float4(ray_d.x, ray_d.y, ray_d.z, 0.0f);
-        st.jitter[slot] = make_float2(jx, jy);
+        PSS(st.ray_o + slot, make_float4(ray_o.x, ray_o.y, ray_o.z, 3.402823466e+38f));    // make_ray's FLT_MAX far clip
+        PSS(st.ray_d + slot, make_float4(ray_d.x, ray_d.y, ray_d.z, 0.0f));
+        PSS(st.jitter + slot, make_float2(jx, jy));
         // Everything else IntegratorState starts with (integrators.cpp:587-600) is a function of the slot, so the first
         // bounce's shading re-derives it instead of reading it back from HBM: throughput = 1, radiance = 0, no previous
         // normal ("specular"), material stack = {air}, the RNG state = this seed advanced by the two draws above
@@ -327,13 +349,13 @@ struct ClosestSrc {        // rays come from the path state (through the active 
     bool store_w;
     BPT_D void load(uint32_t i, V3& o, V3& d, float& max_t, uint32_t& ignored, bool& occ) const {
         uint32_t slot = queue ? queue[i] : i;
-        float4 ro = st.ray_o[slot], rd = st.ray_d[slot];
+        float4 ro = PSL(st.ray_o + slot), rd = PSL(st.ray_d + slot);
         o = v3(ro); d = v3(rd); max_t = ro.w; ignored = 0u;       // intersect_scene passes PrimitiveID 0 (intersection.cpp:608)
         occ = false;
     }
     BPT_D void store(uint32_t i, const HitRecord& h) const {
         uint32_t slot = queue ? queue[i] : i;
-        st.hit[slot] = make_float4(h.t, __uint_as_float(h.prim), __uint_as_float(h.tri), h.v);
+        PSS(st.hit + slot, make_float4(h.t, __uint_as_float(h.prim), __uint_as_float(h.tri), h.v));
         if (store_w) st.hit_w[slot] = h.w;      // barycentric w is only read for meshes with vertex normals
     }
 };
@@ -342,17 +364,17 @@ struct ShadowSrc {         // NEE shadow rays; an unoccluded ray releases its pe
     DPathState st;
     const DShadowItem* items;
     BPT_D void load(uint32_t i, V3& o, V3& d, float& max_t, uint32_t& ignored, bool& occ) const {
-        float4 ro = items[i].o_maxt, rd = items[i].d_light;
+        float4 ro = PSL(&items[i].o_maxt), rd = PSL(&items[i].d_light);
         o = v3(ro); d = v3(rd); max_t = ro.w; ignored = __float_as_uint(rd.w);
         occ = true;
     }
     BPT_D void store(uint32_t i, const HitRecord& h) const {
         if (h.prim == BPT_HIT_MISS) {
-            float4 c = items[i].contrib_slot;
+            float4 c = PSL(&items[i].contrib_slot);
             uint32_t slot = __float_as_uint(c.w);
-            float4 r = st.radiance[slot];
+            float4 r = PSL(st.radiance + slot);
             r.x = r.x + c.x; r.y = r.y + c.y; r.z = r.z + c.z;
-            st.radiance[slot] = r;
+            PSS(st.radiance + slot, r);
         }
     }
 };
@@ -431,13 +453,13 @@ BPT_D uint32_t direction_octant(V3 d) { return (d.x < 0.0f ? 1u : 0u) | (d.y < 0
 BPT_D void shade_path_simple(const DScene& sc, const DPathState& st, const BatchDesc& b, uint32_t bounce, uint32_t slot,
                              bool& alive, uint32_t& octant) {
     const int integrator = sc.settings.integrator;
-    float4 ro4 = st.ray_o[slot], rd4 = st.ray_d[slot], h4 = st.hit[slot];
+    float4 ro4 = PSL(st.ray_o + slot), rd4 = PSL(st.ray_d + slot), h4 = PSL(st.hit + slot);
     V3 ro = v3(ro4), rd = v3(rd4);
     HitRecord h;
     h.t = h4.x; h.prim = __float_as_uint(h4.y); h.tri = __float_as_uint(h4.z); h.v = h4.w; h.w = sc.normals ? st.hit_w[slot] : 0.0f;
     const bool first = bounce == 0;                       // state the ray generation did not write (see k_raygen)
-    V3 throughput = first ? v3(1.0f) : v3(st.throughput[slot]);
-    float4 rad4 = first ? make_float4(0.0f, 0.0f, 0.0f, primary_vignette(sc, rd)) : st.radiance[slot];   // .w carries the vignette to the splat
+    V3 throughput = first ? v3(1.0f) : v3(PSL(st.throughput + slot));
+    float4 rad4 = first ? make_float4(0.0f, 0.0f, 0.0f, primary_vignette(sc, rd)) : PSL(st.radiance + slot);   // .w carries the vignette to the splat
     V3 total = v3(rad4);
     if (b.want_records) { float4 pd = st.primary_d[slot]; pd.w = __uint_as_float(__float_as_uint(pd.w) + 1u); st.primary_d[slot] = pd; }
     alive = false;
@@ -458,7 +480,7 @@ BPT_D void shade_path_simple(const DScene& sc, const DPathState& st, const Batch
             if (m.flags & BPT_MATERIAL_EMISSIVE) {
                 total = total + throughput*m.emission;                                                           // :505-508
             } else {
-                uint4 rng = first ? primary_rng_state(make_sampler(sc, b, slot), b) : st.rng[slot];
+                uint4 rng = first ? primary_rng_state(make_sampler(sc, b, slot), b) : PSL(st.rng + slot);
                 next_set(rng);                                                                                   // random_unilaterals :510
                 float rx = unilateral(rng.x);
                 V2 ryz; ryz.x = unilateral(rng.y); ryz.y = unilateral(rng.z);
@@ -486,16 +508,16 @@ BPT_D void shade_path_simple(const DScene& sc, const DPathState& st, const Batch
                 }
                 alive = bounce + 1 < sc.settings.max_bounce_count;
                 if (alive) {
-                    st.ray_o[slot] = make_float4(next_o.x, next_o.y, next_o.z, 3.402823466e+38f);
-                    st.ray_d[slot] = make_float4(next_d.x, next_d.y, next_d.z, 0.0f);
-                    st.rng[slot] = rng;
-                    st.throughput[slot] = make_float4(throughput.x, throughput.y, throughput.z, 0.0f);
+                    PSS(st.ray_o + slot, make_float4(next_o.x, next_o.y, next_o.z, 3.402823466e+38f));
+                    PSS(st.ray_d + slot, make_float4(next_d.x, next_d.y, next_d.z, 0.0f));
+                    PSS(st.rng + slot, rng);
+                    PSS(st.throughput + slot, make_float4(throughput.x, throughput.y, throughput.z, 0.0f));
                     octant = direction_octant(next_d);
                 }
             }
         }
     }
-    st.radiance[slot] = make_float4(total.x, total.y, total.z, rad4.w);
+    PSS(st.radiance + slot, make_float4(total.x, total.y, total.z, rad4.w));
 }
 
 // One bounce of advanced_integrator (integrators.cpp:612-818) for ONE path: reads the path's state and the hit of its
@@ -505,13 +527,13 @@ BPT_D void shade_path(const DScene& sc, const DPathState& st, const BatchDesc& b
                       bool& alive, bool& want_shadow, DShadowItem& sh, uint32_t& octant) {
     const bpt_settings& set = sc.settings;
     if (set.integrator != BPT_INTEGRATOR_ADVANCED) { shade_path_simple(sc, st, b, bounce, slot, alive, octant); return; }
-    float4 ro4 = st.ray_o[slot], rd4 = st.ray_d[slot], h4 = st.hit[slot];
+    float4 ro4 = PSL(st.ray_o + slot), rd4 = PSL(st.ray_d + slot), h4 = PSL(st.hit + slot);
     V3 ro = v3(ro4), rd = v3(rd4);
     HitRecord h;
     h.t = h4.x; h.prim = __float_as_uint(h4.y); h.tri = __float_as_uint(h4.z); h.v = h4.w; h.w = sc.normals ? st.hit_w[slot] : 0.0f;
     const bool first = bounce == 0;                       // state the ray generation did not write (see k_raygen)
-    V3 throughput = first ? v3(1.0f) : v3(st.throughput[slot]);
-    float4 rad4 = first ? make_float4(0.0f, 0.0f, 0.0f, primary_vignette(sc, rd)) : st.radiance[slot];   // .w carries the vignette to the splat
+    V3 throughput = first ? v3(1.0f) : v3(PSL(st.throughput + slot));
+    float4 rad4 = first ? make_float4(0.0f, 0.0f, 0.0f, primary_vignette(sc, rd)) : PSL(st.radiance + slot);   // .w carries the vignette to the splat
     V3 total = v3(rad4);
     float4 pd = make_float4(0, 0, 0, 0);
     if (b.want_records) pd = st.primary_d[slot];
@@ -523,8 +545,8 @@ BPT_D void shade_path(const DScene& sc, const DPathState& st, const BatchDesc& b
         total_changed = true;
     } else {
         SamplerCtx sm = make_sampler(sc, b, slot);
-        uint4 rng = first ? primary_rng_state(sm, b) : st.rng[slot];
-        float4 pn4 = first ? make_float4(0.0f, 0.0f, 0.0f, __uint_as_float(1u)) : st.prev_n[slot];   // is_specular_bounce starts true
+        uint4 rng = first ? primary_rng_state(sm, b) : PSL(st.rng + slot);
+        float4 pn4 = first ? make_float4(0.0f, 0.0f, 0.0f, __uint_as_float(1u)) : PSL(st.prev_n + slot);   // is_specular_bounce starts true
         V3 prev_N = v3(pn4);
         bool is_specular = (__float_as_uint(pn4.w) & 1u) != 0;
         int stack_at = first ? 0 : (int)st.mstack_at[slot];
@@ -551,8 +573,11 @@ BPT_D void shade_path(const DScene& sc, const DPathState& st, const BatchDesc& b
         MatView mt = load_material(sc, id_t);
 
         if (mi.medium) {                                                                     // :640-649 Beer
-            V3 absorption = v3(exp_f(-mi.absorb.x*t), exp_f(-mi.absorb.y*t), exp_f(-mi.absorb.z*t));
-            throughput = throughput*absorption;
+            // A zero coefficient (the integrator's own "air" is a medium with absorb = 0, :597-599) gives expf(-+0) = 1 and
+            // x*1 = x bit for bit (t is the finite distance of a hit): the three double-precision exps are skipped for it.
+            if (mi.absorb.x != 0.0f) throughput.x = throughput.x*exp_f(-mi.absorb.x*t);
+            if (mi.absorb.y != 0.0f) throughput.y = throughput.y*exp_f(-mi.absorb.y*t);
+            if (mi.absorb.z != 0.0f) throughput.z = throughput.z*exp_f(-mi.absorb.z*t);
         }
 
         if (mt.flags & BPT_MATERIAL_EMISSIVE) {                                              // :651-670
@@ -715,17 +740,17 @@ BPT_D void shade_path(const DScene& sc, const DPathState& st, const BatchDesc& b
 
             if (bounce + 1 >= set.max_bounce_count) alive = false;
             if (alive) {
-                st.ray_o[slot] = make_float4(next_o.x, next_o.y, next_o.z, 3.402823466e+38f);
-                st.ray_d[slot] = make_float4(next_d.x, next_d.y, next_d.z, 0.0f);
-                st.rng[slot] = rng;
-                st.prev_n[slot] = make_float4(N.x, N.y, N.z, __uint_as_float(is_specular ? 1u : 0u));
+                PSS(st.ray_o + slot, make_float4(next_o.x, next_o.y, next_o.z, 3.402823466e+38f));
+                PSS(st.ray_d + slot, make_float4(next_d.x, next_d.y, next_d.z, 0.0f));
+                PSS(st.rng + slot, rng);
+                PSS(st.prev_n + slot, make_float4(N.x, N.y, N.z, __uint_as_float(is_specular ? 1u : 0u)));
                 st.mstack_at[slot] = (uint8_t)stack_at;
-                st.throughput[slot] = make_float4(throughput.x, throughput.y, throughput.z, 0.0f);
+                PSS(st.throughput + slot, make_float4(throughput.x, throughput.y, throughput.z, 0.0f));
                 octant = direction_octant(next_d);
             }
         }
     }
-    if (total_changed || first) st.radiance[slot] = make_float4(total.x, total.y, total.z, rad4.w);
+    if (total_changed || first) PSS(st.radiance + slot, make_float4(total.x, total.y, total.z, rad4.w));
     if (b.want_records) { pd.w = __uint_as_float(ray_count); st.primary_d[slot] = pd; }
 }
 
@@ -782,7 +807,7 @@ k_shade(DScene sc, DPathState st, BatchDesc b, uint32_t bounce,
         if (in_queue) {
             uint32_t key = 0;
             if (have) {
-                uint32_t prim = __float_as_uint(st.hit[slot].y);
+                uint32_t prim = __float_as_uint(PSL(st.hit + slot).y);
                 if (prim != BPT_HIT_MISS) {
                     uint32_t mat = (prim & BPT_HIT_PLANE) ? __ldg(&sc.planes[prim & ~BPT_HIT_PLANE].material)
                                                           : __ldg(&sc.primitives[prim].material);
@@ -830,7 +855,7 @@ k_shade(DScene sc, DPathState st, BatchDesc b, uint32_t bounce,
         }
 
         uint32_t si = queue_append(shadow_count, want_shadow);
-        if (want_shadow) shadow_items[si] = sh;
+        if (want_shadow) { PSS(&shadow_items[si].o_maxt, sh.o_maxt); PSS(&shadow_items[si].d_light, sh.d_light); PSS(&shadow_items[si].contrib_slot, sh.contrib_slot); }
         n_rays += (have ? 1u : 0u) + (want_shadow ? 1u : 0u);
         n_shadow += want_shadow ? 1u : 0u;
         if (block_sort) __syncthreads();
@@ -872,7 +897,7 @@ struct TailSrc {
             o = v3(sh.o_maxt); d = v3(sh.d_light); max_t = sh.o_maxt.w; ignored = __float_as_uint(sh.d_light.w);
             occ = true; has_shadow = false; cur_shadow = true;
         } else {
-            float4 ro = st.ray_o[slot], rd = st.ray_d[slot];
+            float4 ro = PSL(st.ray_o + slot), rd = PSL(st.ray_d + slot);
             o = v3(ro); d = v3(rd); max_t = ro.w; ignored = 0u;
             occ = false; has_closest = false; cur_shadow = false;
         }
@@ -881,12 +906,12 @@ struct TailSrc {
     BPT_D void store(uint32_t, const HitRecord& h) const {
         if (cur_shadow) {
             if (h.prim == BPT_HIT_MISS) {
-                float4 r = st.radiance[slot];
+                float4 r = PSL(st.radiance + slot);
                 r.x = r.x + sh.contrib_slot.x; r.y = r.y + sh.contrib_slot.y; r.z = r.z + sh.contrib_slot.z;
-                st.radiance[slot] = r;
+                PSS(st.radiance + slot, r);
             }
         } else {
-            st.hit[slot] = make_float4(h.t, __uint_as_float(h.prim), __uint_as_float(h.tri), h.v);
+            PSS(st.hit + slot, make_float4(h.t, __uint_as_float(h.prim), __uint_as_float(h.tri), h.v));
             if (store_w) st.hit_w[slot] = h.w;
         }
     }
@@ -946,9 +971,9 @@ k_splat(DScene sc, DPathState st, BatchDesc b, float4* __restrict__ film) {
         float kernel_scale = (float)(sc.filter_lut_size - 1) / (float)sc.filter_radius;
         for (uint32_t s = 0; s < b.S; ++s) {
             uint32_t slot = pix*b.S + s;
-            float4 rad = st.radiance[slot];
+            float4 rad = PSL(st.radiance + slot);
             float vig = rad.w;
-            float2 j = st.jitter[slot];
+            float2 j = PSL(st.jitter + slot);
             V3 c = v3(rad)*vig;
             float wx[SPAN], wy[SPAN];
             #pragma unroll
@@ -989,14 +1014,14 @@ k_splat_generic(DScene sc, DPathState st, BatchDesc b, float4* __restrict__ film
     for (uint32_t slot = blockIdx.x*blockDim.x + threadIdx.x; slot < b.slots; slot += gridDim.x*blockDim.x) {
         uint32_t pix = slot / b.S;
         int x = b.x0 + (int)(pix % b.rect_w), y = __ldg(&b.row_map[b.row0 + pix / b.rect_w]);
-        float4 rad = st.radiance[slot];
+        float4 rad = PSL(st.radiance + slot);
         float vig = rad.w;
         V3 c = v3(rad)*vig;
         if (sc.filter_lut_size == 0) {
             atomicAdd(&film[(size_t)y*sc.film_w + x], make_float4(c.x, c.y, c.z, 1.0f));
             continue;
         }
-        float2 j = st.jitter[slot];
+        float2 j = PSL(st.jitter + slot);
         float kernel_scale = (float)(sc.filter_lut_size - 1) / (float)sc.filter_radius;
         for (int yy = 0; yy <= 2*R; ++yy) {
             int py = y + yy - R;
@@ -1015,7 +1040,7 @@ k_splat_generic(DScene sc, DPathState st, BatchDesc b, float4* __restrict__ film
 
 __global__ void k_write_records(DPathState st, BatchDesc b, bpt_sample_record* __restrict__ out) {
     for (uint32_t slot = blockIdx.x*blockDim.x + threadIdx.x; slot < b.slots; slot += gridDim.x*blockDim.x) {
-        float4 o = st.primary_o[slot], d = st.primary_d[slot], r = st.radiance[slot];
+        float4 o = st.primary_o[slot], d = st.primary_d[slot], r = PSL(st.radiance + slot);
         bpt_sample_record rec;
         rec.ray_o[0] = o.x; rec.ray_o[1] = o.y; rec.ray_o[2] = o.z;
         rec.ray_d[0] = d.x; rec.ray_d[1] = d.y; rec.ray_d[2] = d.z;

@@ -85,3 +85,29 @@ def test_depth_first_numbering_from_subtree_counts():
                 l, r = nd["kids"]
                 nxt += [(l, rank + 1), (r, rank + 1 + l["inner"])]
             level = nxt
+
+
+def test_udiv_magic_is_exact():
+    """make_sampler's slot -> (pixel, sample) and pixel -> (row, column) divisions use a host-computed multiplier
+    (csrc/device_math.cuh udiv_magic, csrc/kernels.cuh set_batch_magic): m = min(2^32 // d, 2^32 - 1), q = (n*m) >> 32,
+    one correction.  Restated here in Python and checked against // and % over edge cases and random operands."""
+    import random
+    rnd = random.Random(3)
+
+    def magic(d):
+        return min((1 << 32) // d, 0xFFFFFFFF)
+
+    def udiv(n, d, m):
+        q = (n * m) >> 32
+        r = n - q * d
+        if r >= d:
+            q += 1
+            r -= d
+        return q, r
+
+    ds = list(range(1, 2050)) + [rnd.randrange(1, 1 << 32) for _ in range(5000)] + [(1 << 31) - 1, 1 << 31, (1 << 32) - 1, 65535, 65536, 65537]
+    for d in ds:
+        m = magic(d)
+        for n in (0, 1, d - 1, d, d + 1, 2 * d - 1, 2 * d, (1 << 32) - 1, 1 << 31, rnd.randrange(1 << 32), rnd.randrange(1 << 32)):
+            if 0 <= n < (1 << 32):
+                assert udiv(n, d, m) == (n // d, n % d), (n, d)
