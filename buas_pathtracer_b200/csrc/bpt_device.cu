@@ -93,6 +93,7 @@ struct bpt_ctx {
     int n_pipes = 2;
     uint32_t min_batches = 0;             // experiment knob (BPT_MIN_BATCHES): at least this many batches per pass
     uint32_t tail_threshold = 65536;      // paths: at or below this many survivors a batch finishes inside k_tail (0 = never)
+    uint32_t shade_late_threads = BPT_SHADE_THREADS;   // block size of k_shade from the second bounce on (its block-wide sort couples the warps of a block)
     uint32_t tail_refill = 8;             // k_tail: idle lanes shade / start their next ray once this many wait (or they are the largest group)
     bool merge_traces = true;
     uint32_t merge_max_slots = 16u << 20; // batches larger than this trace the two populations separately             // trace bounce b's extension rays and bounce b-1's shadow rays in one launch
@@ -346,6 +347,7 @@ int bpt_create(int device, bpt_ctx** out_ctx) {
         if (m > 0) ctx->trace_ctas_per_sm = m;
     }
     if (const char* e = getenv("BPT_REFILL")) { int v = atoi(e); if (v >= 1 && v <= 33) ctx->refill = (uint32_t)v; }
+    if (const char* e = getenv("BPT_SHADE_LATE_THREADS")) { int v = atoi(e); if (v == 32 || v == 64 || v == 128 || v == 256) ctx->shade_late_threads = (uint32_t)std::min(v, BPT_SHADE_THREADS); }
     if (const char* e = getenv("BPT_MERGE_TRACES")) ctx->merge_traces = atoi(e) != 0;
     if (const char* e = getenv("BPT_MERGE_MAX_SLOTS")) { long long v = atoll(e); if (v >= 0 && v <= 0x7FFFFFFFll) ctx->merge_max_slots = (uint32_t)v; }
     if (const char* e = getenv("BPT_TAIL_REFILL")) { int v = atoi(e); if (v >= 1 && v <= 33) ctx->tail_refill = (uint32_t)v; }
@@ -961,7 +963,8 @@ retry_shape:
                     ctx->launches++; ctx->trace_launches++;
                 }
                 begin_span(ctx, ST_SHADE, s);
-                k_shade<<<grid_for(ctx, work, BPT_SHADE_THREADS, BPT_SHADE_MIN_CTAS), BPT_SHADE_THREADS, 0, s>>>(sc, pp.st, b, bounce, in_queue, in_count, b.slots,
+                const uint32_t sh_threads = bounce == 0 ? BPT_SHADE_THREADS : ctx->shade_late_threads;
+                k_shade<<<grid_for(ctx, work, sh_threads, BPT_SHADE_MIN_CTAS*BPT_SHADE_THREADS/sh_threads), sh_threads, 0, s>>>(sc, pp.st, b, bounce, in_queue, in_count, b.slots,
                                                                     pp.q.active[out], counters + out, pp.q.shadow, counters + 2, ctx->d_stats);
                 debug_sync("k_shade", bounce, s);
                 end_span(ctx, s);

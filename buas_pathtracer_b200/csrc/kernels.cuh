@@ -772,6 +772,9 @@ BPT_D void shade_path(const DScene& sc, const DPathState& st, const BatchDesc& b
 #ifndef BPT_SHADE_SORT_BOUNCES
 #define BPT_SHADE_SORT_BOUNCES 64     // bounces < this group their survivors by octant with the block-local sort; later ones append per warp
 #endif
+#ifndef BPT_SHADE_BLOCK_SHADOW
+#define BPT_SHADE_BLOCK_SHADOW 1
+#endif
 #ifndef BPT_SHADE_SORT_MATERIAL
 #define BPT_SHADE_SORT_MATERIAL 0     // measured on B200: shade time C2 +0.8 %, C3 -2.5 %, C4 +4 % -> off (the kernel is bound by
 #endif                                // path-state traffic, not by branch divergence; parity tests pass with it on)
@@ -781,6 +784,7 @@ k_shade(DScene sc, DPathState st, BatchDesc b, uint32_t bounce,
         uint32_t* __restrict__ out_queue, uint32_t* out_count,
         DShadowItem* __restrict__ shadow_items, uint32_t* shadow_count, DStats* stats) {
     __shared__ uint32_t s_count[8], s_start[8], s_base;
+    __shared__ uint32_t s_wshadow[BPT_SHADE_THREADS/32], s_shadow_base;     // shadow-queue append: per-warp counts, the block's base
     __shared__ uint32_t s_slots[BPT_SHADE_THREADS];
     uint32_t n = n_ptr ? *n_ptr : n_fixed;
     uint32_t n_rays = 0, n_shadow = 0;
@@ -835,14 +839,27 @@ k_shade(DScene sc, DPathState st, BatchDesc b, uint32_t bounce,
             // block-local counting sort of the survivors by octant (rank within the octant from a shared-memory atomic)
             uint32_t rank = 0;
             if (alive) rank = atomicAdd(&s_count[octant], 1u);
+            // the shadow queue is appended per block as well, in thread order: one global atomic per block instead of one
+            // per warp on a single address (BPT_SHADE_BLOCK_SHADOW)
+            const uint32_t shadow_mask = __ballot_sync(0xFFFFFFFFu, want_shadow);
+            if (BPT_SHADE_BLOCK_SHADOW && (threadIdx.x & 31u) == 0u) s_wshadow[threadIdx.x >> 5] = __popc(shadow_mask);
             __syncthreads();
             if (threadIdx.x == 0) {
                 uint32_t run = 0;
                 for (int k = 0; k < 8; ++k) { s_start[k] = run; run += s_count[k]; }
                 s_base = run ? atomicAdd(out_count, run) : 0u;
                 s_count[0] = run;                                    // total survivors of this round
+                if (BPT_SHADE_BLOCK_SHADOW) {
+                    uint32_t total_shadow = 0;
+                    for (uint32_t wv = 0; wv < blockDim.x/32; ++wv) { uint32_t c = s_wshadow[wv]; s_wshadow[wv] = total_shadow; total_shadow += c; }
+                    s_shadow_base = total_shadow ? atomicAdd(shadow_count, total_shadow) : 0u;
+                }
             }
             __syncthreads();
+            if (BPT_SHADE_BLOCK_SHADOW && want_shadow) {
+                uint32_t si = s_shadow_base + s_wshadow[threadIdx.x >> 5] + __popc(shadow_mask & ((1u << (threadIdx.x & 31u)) - 1u));
+                PSS(&shadow_items[si].o_maxt, sh.o_maxt); PSS(&shadow_items[si].d_light, sh.d_light); PSS(&shadow_items[si].contrib_slot, sh.contrib_slot);
+            }
             if (alive) s_slots[s_start[octant] + rank] = slot;
             __syncthreads();
             uint32_t total = s_count[0];
@@ -854,8 +871,10 @@ k_shade(DScene sc, DPathState st, BatchDesc b, uint32_t bounce,
             if (alive) out_queue[qi] = slot;
         }
 
-        uint32_t si = queue_append(shadow_count, want_shadow);
-        if (want_shadow) { PSS(&shadow_items[si].o_maxt, sh.o_maxt); PSS(&shadow_items[si].d_light, sh.d_light); PSS(&shadow_items[si].contrib_slot, sh.contrib_slot); }
+        if (!(BPT_SHADE_BLOCK_SHADOW && block_sort)) {
+            uint32_t si = queue_append(shadow_count, want_shadow);
+            if (want_shadow) { PSS(&shadow_items[si].o_maxt, sh.o_maxt); PSS(&shadow_items[si].d_light, sh.d_light); PSS(&shadow_items[si].contrib_slot, sh.contrib_slot); }
+        }
         n_rays += (have ? 1u : 0u) + (want_shadow ? 1u : 0u);
         n_shadow += want_shadow ? 1u : 0u;
         if (block_sort) __syncthreads();
