@@ -287,6 +287,7 @@ def main():
     r.get_stats(reset=True)
     render(0)
     r.sync()
+    settled_rays, settled_bytes = r.ray_prefilter_stats()      # shadow rays a timed pass settles inside k_shade (they never reach a traversal launch)
     st_counts = r.get_stats(reset=True)
     r.stats_enable(False)
     r.film_clear()
@@ -444,17 +445,20 @@ def main():
     #     CUDA-event duration of all those launches in one pass (events on the launching stream).
     peak, peak_src = measured_peaks()
     bytes_closest = algorithmic_bytes(st_counts, shadow=False)
-    bytes_shadow = algorithmic_bytes(st_counts, shadow=True)
+    bytes_shadow = algorithmic_bytes(st_counts, shadow=True) - settled_bytes     # what the traversal LAUNCHES process: the rays k_shade settles are not theirs
     closest_rays = st_counts.rays - st_counts.shadow_rays
     trav_ms = trace_ms + shadow_ms
     achieved = (bytes_closest + bytes_shadow) / (trav_ms * 1e-3) / 1e9 if trav_ms > 0 else None
     roofline = {"bound": "hbm", "kernel": "persistent_trace (all k_trace_closest / k_trace_shadow / k_trace_merged / k_tail launches of a pass)",
                 "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": (achieved / peak) if achieved else None, "traffic": None, "peak_source": peak_src,
-                "algorithmic_bytes_per_ray": (bytes_closest + bytes_shadow) / max(1, st_counts.rays),
+                "algorithmic_bytes_per_ray": (bytes_closest + bytes_shadow) / max(1, st_counts.rays - settled_rays),
                 "algorithmic_bytes_per_launch": (bytes_closest + bytes_shadow) / max(1, trace_launches),
                 "closest_bytes_per_ray": bytes_closest / max(1, closest_rays),
-                "shadow_bytes_per_ray": bytes_shadow / max(1, st_counts.shadow_rays),
+                "shadow_bytes_per_ray": bytes_shadow / max(1, st_counts.shadow_rays - settled_rays),
+                "shadow_rays_settled_in_k_shade": {"rays_per_step": settled_rays, "algorithmic_bytes_excluded": settled_bytes,
+                                                   "what": "NEE shadow rays that never reach a mesh BLAS (plane hit / TLAS root missed / one-leaf TLAS: every item missed or a "
+                                                           "sphere / box hit) are decided inside k_shade; their visits are not counted as traversal-kernel bytes"},
                 "kernel_ms_per_step": trav_ms, "launches_per_step": trace_launches,
                 "avg_launch_ms": trav_ms / max(1, trace_launches),
                 "stage_ms_per_step": {"raygen": raygen_ms, "trace_closest_merged_tail": trace_ms, "shade": shade_ms,

@@ -92,6 +92,7 @@ struct DScene {
     uint32_t filter_lut_size;          // FilterCache::cache_size (0 = Box)
     uint32_t film_w, film_h;
     uint32_t tame_bounds;              // every TLAS/BLAS node box lies inside |x| < 1e15 (enables the FMNMX slab test)
+    uint32_t prefilter;                // k_shade settles the shadow rays that never reach a BLAS itself: 0 off, 1 on, 2 count them only (shadow_tlas_head)
 };
 
 // ---- wavefront path state (SoA, one entry per path slot of the current batch) ------------------------------------
@@ -126,7 +127,8 @@ struct DQueues {
 };
 
 struct DStats {             // device mirror of bpt_stats
-    unsigned long long v[20];   // [0..9] totals as in bpt_stats, [10..16] shadow-only traversal counters
+    unsigned long long v[20];   // [0..9] totals as in bpt_stats, [10..16] shadow-only traversal counters, [17] / [18] shadow rays settled
+                                // inside k_shade and their algorithmic bytes (SURVEY 8d units), counted when shadow_prefilter == 2
 };
 
 } // namespace bpt

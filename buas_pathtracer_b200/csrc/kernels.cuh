@@ -255,6 +255,65 @@ BPT_D uint32_t mstack_get(const DScene& sc, const DPathState& st, const BatchDes
     return level <= 0 ? sc.air_material : (uint32_t)st.mstack[(size_t)(level - 1)*b.slots + slot];
 }
 
+// An NEE shadow ray that never reaches a mesh BLAS is settled where it is generated.  This is the part of
+// intersect_shadow_ray that precedes the first intersect_mesh call -- the planes, the TLAS root, and, when the whole TLAS
+// is one leaf, its spheres / boxes and the root box of each mesh (intersection.cpp:424-454, :456-520) -- executed with the
+// functions the traversal kernels use, in their order, so it decides exactly what persistent_trace would:
+//   2  occluded for certain: a plane is hit (occlusion mode does not return on it, but the ray ends with a hit record whatever
+//      follows), or a sphere / box of the leaf is hit;
+//   1  unoccluded for certain: the TLAS root is missed, or every item of the leaf is missed (mesh: its root box);
+//   0  undecided: a mesh BLAS (or a TLAS with inner nodes, a leaf of more than 7 items, a ray with a zero / denormal / huge
+//      direction component) -> the ray goes to the shadow queue and the traversal kernel starts over with it.
+// In k_shade all 32 lanes run it together; in the traversal kernel the same work is a refill + a TLAS-item step at ~18 of 32
+// lanes, plus 96 bytes of queue traffic per ray.  `bytes`: the algorithmic bytes of the visits made (SURVEY 8d units).
+// (The same test for PRIMARY rays inside k_raygen was measured and dropped: k_raygen 1.7 -> 3.6 ms, bounce-0 traversal
+// 8.0 -> 6.0 ms on C2 -- an even trade, the settled rays were not costing the traversal kernel more than they cost here.)
+BPT_D int shadow_tlas_head(const DScene& sc, V3 o, V3 d, float max_t, uint32_t ignored, uint32_t& bytes) {
+    RayT ray;
+    make_ray(ray, o, d);
+    bytes = 0u;
+    float t = max_t;
+    if (!sc.tame_bounds || !(ray.neg & BPT_RAY_TAME)) return 0;
+    for (uint32_t i = 0; i < sc.plane_count; ++i) {
+        const DPlane& pl = sc.planes[i];
+        if (plane_test(ray, v3(__ldg(&pl.n[0]), __ldg(&pl.n[1]), __ldg(&pl.n[2])), __ldg(&pl.d), t)) return 2;
+    }
+    float tn;
+    bytes = 32u;                                                                                   // the TLAS root is popped
+    const bool root = slab_test(ray, sc.tlas_root_q0.x, sc.tlas_root_q0.y, sc.tlas_root_q0.z, sc.tlas_root_q0.w, sc.tlas_root_q1.x, sc.tlas_root_q1.y, tn);
+    if (!(root && tn < t)) return 1;
+    const uint32_t ref = __float_as_uint(sc.tlas_root_q1.z);
+    if (!(ref & BPT_WREF_LEAF)) return 0;
+    const uint32_t count = (ref >> 28) & 7u, first = ref & BPT_WREF_INDEX_MASK;
+    if (count == 0u) return 0;
+    for (uint32_t k = 0; k < count; ++k) {
+        const uint32_t prim_index = __ldg(&sc.tlas_indices[first + k]);
+        if (prim_index == ignored) continue;
+        const DPrimitive* prim = sc.primitives + prim_index;
+        float4 m[3] = {__ldg(&prim->inv[0]), __ldg(&prim->inv[1]), __ldg(&prim->inv[2])};
+        RayT oray;
+        oray.o = xform(m, ray.o, 1.0f); oray.d = xform(m, ray.d, 0.0f);
+        oray.inv = v3(0.0f); oray.neg = 0u;
+        bytes += 104u;
+        const uint32_t type = __ldg(&prim->type);
+        if (type == BPT_PRIM_SPHERE) {
+            if (sphere_test(oray, __ldg(&prim->sphere_r), t)) return 2;
+        } else {
+            make_ray(oray, oray.o, oray.d);
+            if (!(oray.neg & BPT_RAY_TAME)) return 0;
+            if (type == BPT_PRIM_BOX) {
+                if (box_test(oray, __ldg(&prim->box_r[0]), __ldg(&prim->box_r[1]), __ldg(&prim->box_r[2]), t)) return 2;
+            } else if (type == BPT_PRIM_MESH) {
+                const DMesh* mesh = sc.meshes + __ldg(&prim->mesh);
+                float4 q0 = __ldg(&mesh->root_q0), q1 = __ldg(&mesh->root_q1);
+                bytes += 32u;                                                                      // the BLAS root is popped
+                if (slab_test(oray, q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, tn) && tn < t) return 0;
+            }
+        }
+    }
+    return 1;
+}
+
 // ---- kernels ---------------------------------------------------------------------------------------------------------------
 
 // render_tile's per-sample ray setup (raytracer.cpp:372-461) with per-pixel counter-based seeding
@@ -523,8 +582,11 @@ BPT_D void shade_path_simple(const DScene& sc, const DPathState& st, const Batch
 // One bounce of advanced_integrator (integrators.cpp:612-818) for ONE path: reads the path's state and the hit of its
 // current ray, accumulates emission / sky, draws the next direction, and reports whether the path continues
 // (its next ray is then in st.ray_o/ray_d) and whether it queued an NEE shadow ray (`sh`).
+// PRE: compile the shadow-ray prefilter in (k_shade<true>, launched for scenes whose TLAS is one leaf -- elsewhere it
+// decides next to nothing and its registers cost k_shade 3 %).
+template <bool PRE>
 BPT_D void shade_path(const DScene& sc, const DPathState& st, const BatchDesc& b, uint32_t bounce, uint32_t slot,
-                      bool& alive, bool& want_shadow, DShadowItem& sh, uint32_t& octant) {
+                      bool& alive, bool& want_shadow, DShadowItem& sh, uint32_t& octant, uint32_t& settled_shadow, uint32_t& settled_bytes) {
     const bpt_settings& set = sc.settings;
     if (set.integrator != BPT_INTEGRATOR_ADVANCED) { shade_path_simple(sc, st, b, bounce, slot, alive, octant); return; }
     float4 ro4 = PSL(st.ray_o + slot), rd4 = PSL(st.ray_d + slot), h4 = PSL(st.hit + slot);
@@ -750,6 +812,19 @@ BPT_D void shade_path(const DScene& sc, const DPathState& st, const BatchDesc& b
             }
         }
     }
+    if (PRE && want_shadow && sc.prefilter) {
+        // settle the shadow ray here when it never reaches a BLAS (shadow_tlas_head): its contribution joins `total` behind this
+        // bounce's other terms, which is where the traversal kernel's store would have added it
+        uint32_t bytes;
+        const int verdict = shadow_tlas_head(sc, v3(sh.o_maxt), v3(sh.d_light), sh.o_maxt.w, __float_as_uint(sh.d_light.w), bytes);
+        if (verdict != 0) {
+            settled_shadow = 1u; settled_bytes = bytes;
+            if (sc.prefilter == 1u) {
+                want_shadow = false;
+                if (verdict == 1) { total = total + v3(sh.contrib_slot); total_changed = true; }
+            }
+        }
+    }
     if (total_changed || first) PSS(st.radiance + slot, make_float4(total.x, total.y, total.z, rad4.w));
     if (b.want_records) { pd.w = __uint_as_float(ray_count); st.primary_d[slot] = pd; }
 }
@@ -778,6 +853,7 @@ BPT_D void shade_path(const DScene& sc, const DPathState& st, const BatchDesc& b
 #ifndef BPT_SHADE_SORT_MATERIAL
 #define BPT_SHADE_SORT_MATERIAL 0     // measured on B200: shade time C2 +0.8 %, C3 -2.5 %, C4 +4 % -> off (the kernel is bound by
 #endif                                // path-state traffic, not by branch divergence; parity tests pass with it on)
+template <bool PRE>
 __global__ void __launch_bounds__(BPT_SHADE_THREADS, BPT_SHADE_MIN_CTAS)
 k_shade(DScene sc, DPathState st, BatchDesc b, uint32_t bounce,
         const uint32_t* __restrict__ in_queue, const uint32_t* __restrict__ n_ptr, uint32_t n_fixed,
@@ -788,6 +864,7 @@ k_shade(DScene sc, DPathState st, BatchDesc b, uint32_t bounce,
     __shared__ uint32_t s_slots[BPT_SHADE_THREADS];
     uint32_t n = n_ptr ? *n_ptr : n_fixed;
     uint32_t n_rays = 0, n_shadow = 0;
+    unsigned long long n_settled = 0, n_settled_bytes = 0;
 
     for (uint32_t blk0 = blockIdx.x*blockDim.x; blk0 < n; blk0 += gridDim.x*blockDim.x) {
         uint32_t i = blk0 + threadIdx.x;
@@ -834,7 +911,8 @@ k_shade(DScene sc, DPathState st, BatchDesc b, uint32_t bounce,
             __syncthreads();
         }
 #endif
-        if (have) shade_path(sc, st, b, bounce, slot, alive, want_shadow, sh, octant);
+        uint32_t settled = 0u, settled_bytes = 0u;   // a shadow ray shade_path settled itself (counted as a traced ray all the same)
+        if (have) shade_path<PRE>(sc, st, b, bounce, slot, alive, want_shadow, sh, octant, settled, settled_bytes);
         if (block_sort) {
             // block-local counting sort of the survivors by octant (rank within the octant from a shared-memory atomic)
             uint32_t rank = 0;
@@ -875,11 +953,18 @@ k_shade(DScene sc, DPathState st, BatchDesc b, uint32_t bounce,
             uint32_t si = queue_append(shadow_count, want_shadow);
             if (want_shadow) { PSS(&shadow_items[si].o_maxt, sh.o_maxt); PSS(&shadow_items[si].d_light, sh.d_light); PSS(&shadow_items[si].contrib_slot, sh.contrib_slot); }
         }
-        n_rays += (have ? 1u : 0u) + (want_shadow ? 1u : 0u);
-        n_shadow += want_shadow ? 1u : 0u;
+        const uint32_t settled_here = sc.prefilter == 1u ? settled : 0u;     // mode 2 only classifies: the ray is in the queue as well
+        n_rays += (have ? 1u : 0u) + (want_shadow ? 1u : 0u) + settled_here;
+        n_shadow += (want_shadow ? 1u : 0u) + settled_here;
+        n_settled += settled; n_settled_bytes += settled_bytes;
         if (block_sort) __syncthreads();
     }
     flush_ray_counts(stats, n_rays, n_shadow);
+    if (sc.prefilter == 2u) {             // the counting pass: how many shadow rays a timed pass settles in here, and their bytes
+        #pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { n_settled += __shfl_xor_sync(0xFFFFFFFFu, n_settled, o); n_settled_bytes += __shfl_xor_sync(0xFFFFFFFFu, n_settled_bytes, o); }
+        if ((threadIdx.x & 31) == 0 && n_settled) { atomicAdd(&stats->v[17], n_settled); atomicAdd(&stats->v[18], n_settled_bytes); }
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -905,9 +990,10 @@ struct TailSrc {
         if (!has_shadow && !has_closest) {
             bool cont = false, want_shadow = false;
             uint32_t octant_unused = 0;
-            shade_path(*sc, st, *b, bounce, slot, cont, want_shadow, sh, octant_unused);
-            n_rays += 1u + (want_shadow ? 1u : 0u);
-            n_shadow += want_shadow ? 1u : 0u;
+            uint32_t settled = 0u, settled_bytes_unused = 0u;
+            shade_path<false>(*sc, st, *b, bounce, slot, cont, want_shadow, sh, octant_unused, settled, settled_bytes_unused);     // the few shadow rays of a tail all go through its own traversal
+            n_rays += 1u + (want_shadow ? 1u : 0u) + settled;          // k_tail never runs in the counting mode (shadow_prefilter is 0 or 1 here)
+            n_shadow += (want_shadow ? 1u : 0u) + settled;
             ++bounce;
             has_shadow = want_shadow; has_closest = cont; alive = cont;
             if (!want_shadow && !cont) return false;

@@ -92,6 +92,10 @@ def load_library():
     L.bpt_stats_enable.argtypes = [vp, C.c_int]
     L.bpt_get_stats.restype = C.c_int
     L.bpt_get_stats.argtypes = [vp, P(capi.Stats), C.c_int]
+    L.bpt_set_ray_prefilter.restype = C.c_int
+    L.bpt_set_ray_prefilter.argtypes = [vp, C.c_int]
+    L.bpt_get_ray_prefilter_stats.restype = C.c_int
+    L.bpt_get_ray_prefilter_stats.argtypes = [vp, P(C.c_uint64)]
     L.bpt_get_pass_timing.restype = C.c_int
     L.bpt_get_pass_timing.argtypes = [vp, P(capi.PassTiming)]
     L.bpt_set_detailed_timing.restype = C.c_int
@@ -388,6 +392,16 @@ class Renderer:
         st = capi.Stats()
         _check(self.lib.bpt_get_stats(self.handle, C.byref(st), int(reset)), "bpt_get_stats")
         return st
+
+    def set_ray_prefilter(self, on=True):
+        _check(self.lib.bpt_set_ray_prefilter(self.handle, int(on)), "bpt_set_ray_prefilter")
+
+    def ray_prefilter_stats(self):
+        """(rays, algorithmic bytes) of the shadow rays the shading kernel settles itself, as counted by the last pass(es) rendered
+        with stats_enable(True); read before get_stats(reset=True)"""
+        out = (C.c_uint64 * 2)()
+        _check(self.lib.bpt_get_ray_prefilter_stats(self.handle, out), "bpt_get_ray_prefilter_stats")
+        return int(out[0]), int(out[1])
 
     def set_detailed_timing(self, on=True):
         _check(self.lib.bpt_set_detailed_timing(self.handle, int(on)), "bpt_set_detailed_timing")

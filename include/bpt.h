@@ -364,6 +364,13 @@ BPT_API int bpt_set_sample_records(bpt_ctx* ctx, bpt_sample_record* host_records
 /* rays / shadow_rays / samples are always counted; the traversal counters need the counting instantiations. */
 BPT_API int bpt_stats_enable(bpt_ctx* ctx, int enable);
 BPT_API int bpt_get_stats(bpt_ctx* ctx, bpt_stats* out, int reset);
+/* Shadow rays that never reach a mesh BLAS (planes / TLAS root / the spheres, boxes and mesh root boxes of a one-leaf TLAS
+ * decide them: the head of intersect_shadow_ray, intersection.cpp:424-520) are settled inside the shading kernel and never
+ * enter the traversal kernels.  bpt_set_ray_prefilter(0) turns that off.  A pass rendered with bpt_stats_enable(1)
+ * traces every shadow ray in the traversal kernels (so that bpt_stats stays in the reference's units) and only counts the
+ * rays a normal pass would settle early: out[0] = their number, out[1] = their algorithmic bytes (SURVEY 8d units). */
+BPT_API int bpt_set_ray_prefilter(bpt_ctx* ctx, int enable);
+BPT_API int bpt_get_ray_prefilter_stats(bpt_ctx* ctx, uint64_t out[2]);
 /* GPU time of the last render pass by stage, measured with CUDA events on the context's stream (ms). */
 typedef struct bpt_pass_timing {
     float total_ms, raygen_ms, trace_ms, shade_ms, shadow_ms, splat_ms;
