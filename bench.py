@@ -67,6 +67,11 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append([c.strip() for c in line.split(",")])
 
+    def mark(self):
+        """the timed region starts here: only samples taken from now on are reported (nvidia-smi needs ~0.2 s to come up, so it is
+        started ahead of the warm-up)"""
+        self.first = len(self.rows)
+
     def stop(self):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
@@ -76,7 +81,7 @@ class ClockSampler:
         except subprocess.TimeoutExpired:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
-        for r in self.rows:
+        for r in self.rows[getattr(self, "first", 0):]:
             try:
                 sm.append(float(r[0])); mx.append(float(r[1]))
             except (ValueError, IndexError):
@@ -162,7 +167,7 @@ def cpu_reference_run(cfg_key, w, h, seconds_target=15.0, threads=None, ref=None
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--config", default="c2")
@@ -292,6 +297,8 @@ def main():
     r.stats_enable(False)
     r.film_clear()
 
+    clocks = ClockSampler(local_rank)
+    clocks.start()
     for i in range(args.warmup):                      # enqueued back to back like the timed steps (same batch shapes, path state allocated)
         step(i * spp)
     r.sync()
@@ -303,10 +310,9 @@ def main():
 
     # --- timed region: K steps, CUDA events on this rank, max over ranks ---
     r.get_stats(reset=True)
-    clocks = ClockSampler(local_rank)
-    clocks.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
+    clocks.mark()
     ev0.record()
     trace_ms = shadow_ms = shade_ms = splat_ms = raygen_ms = 0.0
     launches = trace_launches = 0
