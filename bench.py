@@ -484,9 +484,12 @@ def main():
     traffic_file = os.path.join(ROOT, "profiles", "trace_dram_bytes.json")
     if os.path.exists(traffic_file) and args.config == "c2" and world == 1:     # measured for exactly this workload
         tf = json.load(open(traffic_file))
-        roofline["traffic"] = tf.get("dram_bytes_per_launch")
+        # per launch like `achieved`: the capture's bytes per PASS over this run's launches per pass (the capture ran with a host wait per
+        # pass, which splits a pass over both batch streams: twice the launches, the same rays)
+        roofline["traffic"] = tf.get("dram_bytes_per_pass", 0) / max(1, trace_launches)
+        roofline["traffic_per_pass"] = tf.get("dram_bytes_per_pass")
         roofline["traffic_source"] = tf.get("source")
-        roofline["l2_bytes_per_launch"] = tf.get("l2_bytes_per_pass", 0) / max(1, tf.get("trace_launches_per_pass", 1))
+        roofline["l2_bytes_per_launch"] = tf.get("l2_bytes_per_pass", 0) / max(1, trace_launches)
         mfile = os.path.join(ROOT, "profiles", "r2_trace_metrics.json")
         if os.path.exists(mfile):                                              # from the committed ncu capture of this workload
             tm = json.load(open(mfile))

@@ -808,7 +808,10 @@ static int render_rows(bpt_ctx* ctx, int32_t x0, int32_t x1, const std::vector<i
     int n_pipes = (ctx->detailed_timing || want_records) ? 1 : ctx->n_pipes;
 
     // batch shape
-    uint64_t cap = 64ull << 20;        // 64 Mi path slots per pipeline (~23 GB of path state each): few, large batches
+    // 128 Mi path slots per pipeline (~30 GB of path state each at 12 bounces): few, large batches.  Every launch of a batch ends with
+    // the machine draining behind its longest rays, so fewer, larger launches win: pass period of C2 / C3 at 64 spp / C4 at 64 spp with a
+    // cap of 32 / 64 / 128 Mi slots: 54.2 / 52.4 / 50.7 ms, - / 107.6 / 105.6, - / 51.5 / 50.4.  Out of device memory halves the cap (below).
+    uint64_t cap = 128ull << 20;
     if (const char* e = getenv("BPT_MAX_SLOTS")) { uint64_t v = strtoull(e, nullptr, 10); if (v >= 1024) cap = v; }
     uint32_t S, rows_per_batch;
     uint64_t n_batches;

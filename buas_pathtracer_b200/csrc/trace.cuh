@@ -179,7 +179,7 @@ struct TraceCounters {   // per-thread, flushed by the caller
 #endif
 #define BPT_TRACE_THREADS 128     // block size of every kernel that runs persistent_trace
 #ifndef BPT_TRIP_LIMIT
-#define BPT_TRIP_LIMIT (1u << 28) // scheduling-loop trips per warp; ~400x the largest legitimate count (a 64 Mi-slot batch)
+#define BPT_TRIP_LIMIT (1u << 28) // scheduling-loop trips per warp; ~200x the largest legitimate count (a 128 Mi-slot batch)
 #endif
 
 // MODE: 0 = closest hit (intersect_scene), 1 = occlusion (intersect_shadow_ray), 2 = per ray (Src::load says which)
