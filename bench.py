@@ -489,6 +489,10 @@ def main():
         roofline["traffic"] = tf.get("dram_bytes_per_pass", 0) / max(1, trace_launches)
         roofline["traffic_per_pass"] = tf.get("dram_bytes_per_pass")
         roofline["traffic_source"] = tf.get("source")
+        if achieved and roofline["traffic"] and roofline["traffic"] < 0.5*roofline["algorithmic_bytes_per_launch"]:
+            roofline["note"] = ("`achieved` counts ALGORITHMIC bytes (SURVEY 8d convention); the measured DRAM traffic of these launches is "
+                                f"{roofline['traffic']/roofline['algorithmic_bytes_per_launch']:.0%} of them -- the acceleration structure is served from L2 -- so the "
+                                "fraction can exceed 1 and the kernel's actual bound is issue slots (issue_active_pct, active_lanes_of_32; DESIGN.md 4.1)")
         roofline["l2_bytes_per_launch"] = tf.get("l2_bytes_per_pass", 0) / max(1, trace_launches)
         mfile = os.path.join(ROOT, "profiles", "r2_trace_metrics.json")
         if os.path.exists(mfile):                                              # from the committed ncu capture of this workload
