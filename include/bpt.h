@@ -328,8 +328,10 @@ BPT_API int bpt_host_unregister(void* host_ptr);
 
 /* One progressive pass over the pixel rect [x0,x1) x [y0,y1): what render_all_tiles + every
  * render_tile call of the pass do (raytracer.cpp:366-495, :692-757).  `frame_count` is
- * AccumulationBuffer::frame_count (sample_index = frame_count + s).  Asynchronous on the context's
- * stream; bpt_sync() or bpt_download_film() waits. */
+ * AccumulationBuffer::frame_count (sample_index = frame_count + s).  Asynchronous; bpt_sync() or
+ * bpt_download_film() waits.  Passes enqueued without a wait in between overlap on the device (the
+ * next pass starts under the kernel tails of the previous one); every reader / clear of the film
+ * issued between two passes still sees exactly the passes issued before it. */
 BPT_API int bpt_render_pass(bpt_ctx* ctx, int32_t x0, int32_t y0, int32_t x1, int32_t y1,
                             uint32_t frame_count, uint32_t spp, uint32_t seed_mode, uint32_t seed_salt);
 /* Same pass over a set of row bands [y0,y1) x [x0,x1) (n_bands pairs in y0y1) treated as ONE workload: the rows a
