@@ -297,6 +297,30 @@ def test_render_parity_settings_variants(renderer, bpt, oracle):
     _check_film(film, rfilm, "C1 gaussian-3 filter")
 
 
+@pytest.mark.parametrize("name", ["Gaussian 12", "Lanczos 3", "Lanczos 4", "Lanczos 6", "Lanczos 12"])
+def test_wide_reconstruction_filters_on_device(renderer, bpt, oracle, name):
+    """g_filters[] beyond the default (reconstruction_filters.cpp:97-106): splats of radius 3, 4, 6 and 12 pixels -- up to 625 film
+    updates per sample, negative lobes included (Lanczos) -- through k_splat_generic against the reference's splat_filter.  The
+    radius-12 footprints cross the whole 48-row band that is rendered here, and its borders."""
+    w, h = 96, 64
+    a, b = build_both(bpt, oracle, scenes.c1_week3, w, h)
+    for s in (a, b):
+        s.load_reconstruction_kernel(name)
+    rect, spp = (8, 8, 88, 56), 2
+    renderer.upload_scene(a)
+    renderer.film_resize(w, h)
+    renderer.render_pass(spp, rect=rect)
+    film = renderer.download_film()
+    rfilm, _ = b.render_parity(w, h, spp, rect=rect, records=True)
+    # weights of a Lanczos kernel change sign: compare them absolutely, scaled by the largest weight sum of the film
+    wg, wr = film[..., 3].astype(np.float64), rfilm[..., 3].astype(np.float64)
+    assert np.allclose(wg, wr, rtol=0, atol=2e-5 * float(np.abs(wr).max())), f"{name}: filter weight sums differ"
+    assert np.count_nonzero(wr[:8]) > 0 and np.count_nonzero(wr[:, :8]) > 0, "the footprint must reach outside the rendered rect"
+    e = rel_rmse(film[..., :3].astype(np.float64), rfilm[..., :3].astype(np.float64))
+    print(f"C1 {name}: film relRMSE {e:.3g}")
+    assert e <= FILM_REL_RMSE, f"{name}: film relRMSE {e}"
+
+
 def test_subrect_and_row_sharding_is_partition_independent(renderer, c1, bpt, oracle):
     """rendering the image as row bands (the multi-GPU partition) sums to the full-frame film"""
     a, b = build_both(bpt, oracle, scenes.c1_week3, 160, 90)
