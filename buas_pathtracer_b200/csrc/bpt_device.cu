@@ -133,19 +133,6 @@ struct bpt_ctx {
 
 namespace {
 
-template <typename T>
-int upload(bpt_ctx* ctx, const T* host, size_t count, const T** out, std::vector<void*>* owner) {
-    *out = nullptr;
-    size_t bytes = std::max<size_t>(count*sizeof(T), 256);
-    void* d = nullptr;
-    CK(cudaMalloc(&d, bytes));
-    owner->push_back(d);
-    if (count) CK(cudaMemcpyAsync(d, host, count*sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
-    ctx->h2d_bytes += count*sizeof(T);
-    *out = (const T*)d;
-    return BPT_OK;
-}
-
 int device_slot(bpt_ctx::Slot* slots, int id, size_t bytes, void** out) {
     bpt_ctx::Slot& sl = slots[id];
     bytes = std::max<size_t>(bytes, 256);
