@@ -91,6 +91,8 @@ struct bpt_ctx {
         uint64_t d_record_capacity = 0;
     } pipes[BPT_MAX_PIPES];
     int n_pipes = 2;
+    bool pipes_forced = false;            // BPT_PIPES given: no automatic widening for small batches
+    uint64_t wide_pipes_budget = 64ull << 30;   // bytes of path state that four batch streams may hold together (see render_rows)
     uint32_t min_batches = 0;             // experiment knob (BPT_MIN_BATCHES): at least this many batches per pass
     uint32_t tail_threshold = 65536;      // paths: at or below this many survivors a batch finishes inside k_tail (0 = never)
     uint32_t shade_late_threads = BPT_SHADE_THREADS;   // block size of k_shade from the second bounce on (its block-wide sort couples the warps of a block)
@@ -341,7 +343,8 @@ int bpt_create(int device, bpt_ctx** out_ctx) {
     if (const char* e = getenv("BPT_MERGE_MAX_SLOTS")) { long long v = atoll(e); if (v >= 0 && v <= 0x7FFFFFFFll) ctx->merge_max_slots = (uint32_t)v; }
     if (const char* e = getenv("BPT_TAIL_REFILL")) { int v = atoi(e); if (v >= 1 && v <= 33) ctx->tail_refill = (uint32_t)v; }
     if (const char* e = getenv("BPT_TAIL_THRESHOLD")) { long v = atol(e); if (v >= 0 && v <= (1 << 22)) ctx->tail_threshold = (uint32_t)v; }
-    if (const char* e = getenv("BPT_PIPES")) { int v = atoi(e); if (v >= 1 && v <= BPT_MAX_PIPES) ctx->n_pipes = v; }
+    if (const char* e = getenv("BPT_PIPES")) { int v = atoi(e); if (v >= 1 && v <= BPT_MAX_PIPES) { ctx->n_pipes = v; ctx->pipes_forced = true; } }
+    if (const char* e = getenv("BPT_WIDE_PIPES_GB")) ctx->wide_pipes_budget = strtoull(e, nullptr, 10) << 30;
     if (const char* e = getenv("BPT_MIN_BATCHES")) { int v = atoi(e); if (v >= 1 && v <= 64) ctx->min_batches = (uint32_t)v; }
     if (const char* e = getenv("BPT_TRACE_CTAS")) { int v = atoi(e); if (v >= 1 && v <= 32) ctx->trace_ctas_per_sm = v; }
     const char* dt = getenv("BPT_DETAILED_TIMING");
@@ -838,6 +841,15 @@ retry_shape:
     }
     uint64_t slots64 = (uint64_t)rect_w*rows_per_batch*S;
     if (slots64 > 0x7FFFFFFFull) { set_error("%s: batch too large", who); return BPT_ERR_ARG; }
+    // One-batch passes enqueued back to back (a rank's share of a multi-GPU frame) go round BPT_MAX_PIPES streams instead of two
+    // when the path state of that many batches stays within a budget (64 GB): more passes in flight under each other's chains of
+    // small launches.  Pass period of an 8 / 4 / 2-rank share of C2 with 2 -> 4 streams: 7.36 -> 7.00, 13.78 -> 13.37, 26.18 -> 25.63 ms
+    // (the whole frame: 50.77 -> 50.18 at 123 GB of path state -- not taken).
+    {
+        const uint64_t levels = std::min<uint32_t>(BPT_MATERIAL_STACK_DEPTH - 1, std::max<uint32_t>(1, ctx->sc.settings.max_bounce_count));
+        const uint64_t state_bytes = slots64*(197ull + 2ull*levels);          // ensure_state: the arrays of one pipeline
+        if (back_to_back && n_batches == 1 && !ctx->pipes_forced && (uint64_t)BPT_MAX_PIPES*state_bytes <= ctx->wide_pipes_budget) n_pipes = BPT_MAX_PIPES;
+    }
     for (int p = 0; p < n_pipes; ++p) {
         const uint32_t levels = std::min<uint32_t>(BPT_MATERIAL_STACK_DEPTH - 1, std::max<uint32_t>(1, ctx->sc.settings.max_bounce_count));
         int rc = ensure_state(ctx, &ctx->pipes[p], (uint32_t)slots64, levels, want_records);
