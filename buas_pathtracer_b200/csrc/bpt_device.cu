@@ -92,7 +92,7 @@ struct bpt_ctx {
     } pipes[BPT_MAX_PIPES];
     int n_pipes = 2;
     bool pipes_forced = false;            // BPT_PIPES given: no automatic widening for small batches
-    uint64_t wide_pipes_budget = 64ull << 30;   // bytes of path state that four batch streams may hold together (see render_rows)
+    uint64_t wide_pipes_budget = 32ull << 30;   // bytes of path state that four batch streams may hold together (see render_rows)
     uint32_t min_batches = 0;             // experiment knob (BPT_MIN_BATCHES): at least this many batches per pass
     uint32_t tail_threshold = 65536;      // paths: at or below this many survivors a batch finishes inside k_tail (0 = never)
     uint32_t shade_late_threads = BPT_SHADE_THREADS;   // block size of k_shade from the second bounce on (its block-wide sort couples the warps of a block)
@@ -842,9 +842,10 @@ retry_shape:
     uint64_t slots64 = (uint64_t)rect_w*rows_per_batch*S;
     if (slots64 > 0x7FFFFFFFull) { set_error("%s: batch too large", who); return BPT_ERR_ARG; }
     // One-batch passes enqueued back to back (a rank's share of a multi-GPU frame) go round BPT_MAX_PIPES streams instead of two
-    // when the path state of that many batches stays within a budget (64 GB): more passes in flight under each other's chains of
-    // small launches.  Pass period of an 8 / 4 / 2-rank share of C2 with 2 -> 4 streams: 7.36 -> 7.00, 13.78 -> 13.37, 26.18 -> 25.63 ms
-    // (the whole frame: 50.77 -> 50.18 at 123 GB of path state -- not taken).
+    // when the path state of that many batches stays within a budget (32 GB): more passes in flight under each other's chains of
+    // small launches.  Pass period of an 8 / 4-rank share of C2 on one GPU with 2 -> 4 streams: 7.36 -> 7.11, 13.78 -> 13.43 ms; on
+    // 8 / 4 GPUs 7.73 -> 7.49, 14.06 -> 13.93 ms.  Larger batches stay on two streams: a 2-rank share gained 2 % on one GPU and
+    // nothing on two GPUs for 59 GB of path state, the whole frame 1.2 % for 123 GB.
     {
         const uint64_t levels = std::min<uint32_t>(BPT_MATERIAL_STACK_DEPTH - 1, std::max<uint32_t>(1, ctx->sc.settings.max_bounce_count));
         const uint64_t state_bytes = slots64*(197ull + 2ull*levels);          // ensure_state: the arrays of one pipeline
