@@ -7,12 +7,15 @@ A *step* is one progressive pass (render_all_tiles, Raytracer/raytracer.cpp:692-
 every pixel of the frame x its samples-per-pixel through ray generation, TLAS/BLAS traversal, shading/NEE,
 Russian roulette and the Mitchell-Netravali splat.  N=1 renders BASELINE config 2 (1,310,720-triangle displaced
 icosphere, 1920x1080, 64 spp).  With N>1 (torchrun, one rank per GPU) the same frame is split into interleaved
-64-row blocks over the ranks, the scene is replicated, and the partial films are summed with ONE NCCL reduce per
+8-row blocks over the ranks, the scene is replicated, and the partial films are summed with ONE NCCL reduce per
 pass by the library itself (bpt_reduce_film, include/bpt.h section 3; strong scaling).
+The K timed steps are enqueued back to back and waited for once (barrier + synchronize on both sides of the K steps):
+the library overlaps consecutive passes on the device and keeps every film reader ordered.
 
 `value`     device-timed whole-job Mrays/s with the scene resident in HBM (CUDA events, max over ranks).
 `e2e`       the same metric through the public C-ABI with host buffers: every step re-uploads the host scene
-            (bpt_upload_scene: flatten + H2D), renders, and downloads the film (D2H) inside the timed region.
+            (bpt_upload_scene_async: flatten + H2D), renders, and reads the film back (bpt_download_film_async: D2H)
+            inside the timed region; the copies of neighbouring steps overlap the rendering.
 `roofline`  persistent_trace (all traversal launches): algorithmic bytes (reference binary-BVH visit counts x SURVEY 8d
             byte sizes) / their summed launch time, against the measured HBM bandwidth.
 `cpu_baseline` / `--impl reference`: the reference's own tile-multithreaded CPU renderer (oracle/_ref, built from
